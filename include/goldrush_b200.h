@@ -1,0 +1,273 @@
+/*
+ * goldrush_b200.h — C ABI of libgoldrush_b200.so, the B200 (sm_100a) engine behind GoldRush-Path's
+ * read-selection loop.  Plain pointers and sizes only; every device allocation lives behind the
+ * opaque grb_ctx.  All citations are file:line under the reference tree (bcgsc/goldrush v1.2.2).
+ *
+ * The reference has no FFI; the seams below are the function boundaries inside
+ * goldrush_path/goldrush_path.cpp that a maintainer would re-point at this library
+ * (see INTEGRATION.md for the binding on the reference side).
+ *
+ * Conventions: every call returns 0 on success and a negative grb_status otherwise;
+ * grb_last_error(ctx) gives the message.  A context is single-threaded (one host thread drives it)
+ * and owns one CUDA device.  Nothing here falls back to a CPU implementation: without a usable
+ * CUDA device grb_create fails with GRB_ERR_CUDA.
+ */
+#ifndef GOLDRUSH_B200_H
+#define GOLDRUSH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct grb_ctx grb_ctx;
+
+typedef enum grb_status
+{
+  GRB_OK = 0,
+  GRB_ERR_ARG = -1,    /* invalid argument / option (reference: opt.cpp:176-215 -> exit(1)) */
+  GRB_ERR_CUDA = -2,   /* CUDA runtime error or no device */
+  GRB_ERR_STATE = -3,  /* call out of order (e.g. query before grb_finalize_bitvector) */
+  GRB_ERR_FORMAT = -4, /* input is not FASTQ (reference: goldrush_path.cpp:247-250) */
+  GRB_ERR_NOMEM = -5
+} grb_status;
+
+/* ---- options: one field per opt:: global (goldrush_path/opt.hpp:9-38, defaults opt.cpp:5-32) ---- */
+typedef struct grb_params
+{
+  uint64_t assigned_max;   /* -a */
+  uint64_t unassigned_min; /* -u */
+  uint64_t tile_length;    /* -t */
+  uint64_t block_size;     /* -b */
+  uint64_t hash_universe;  /* -H (0 = derive, goldrush_path.cpp:1109-1123) */
+  uint64_t genome_size;    /* -g */
+  uint64_t kmer_size;      /* -k */
+  uint64_t weight;         /* -w */
+  uint64_t min_length;     /* -m */
+  uint64_t hash_num;       /* -h */
+  double occupancy;        /* -o */
+  double ratio;            /* -r */
+  uint64_t max_paths;      /* -M */
+  uint64_t threshold;      /* -x */
+  uint32_t phred_min;      /* -P (already resolved: never 0 when pass 1 starts) */
+  uint32_t phred_delta;    /* -d */
+  int32_t silver_path;     /* --silver_path */
+  int32_t device;          /* CUDA device ordinal */
+  const char* const* seeds; /* hash_num NUL-terminated strings from grb_make_seed_pattern */
+} grb_params;
+
+/* Fills the reference's defaults (opt.cpp:5-32); seeds = NULL, device = 0. */
+void grb_params_default(grb_params* p);
+
+/* ---- host-side scalar helpers (no device) ---- */
+
+/* spaced_seeds.cpp:7-68 make_seed_pattern.  out[i] must hold k + h bytes.  preset may be "" / NULL
+ * (random design, srand(123) + rand()%2 exactly as the reference). */
+int grb_make_seed_pattern(const char* preset, unsigned k, unsigned weight, unsigned h, char** out);
+/* MIBloomFilter.hpp:94-101 calcOptimalSize */
+uint64_t grb_calc_optimal_size(uint64_t entries, unsigned hash_num, double occupancy);
+/* goldrush_path.cpp:1114-1121 default hash universe */
+uint64_t grb_default_hash_universe(uint64_t weight, uint64_t genome_size, uint64_t hash_num);
+/* calc_phred_average.cpp:32-42: final log10 / casts from the two running sums the device returns */
+void grb_phred_finalize(double first_half_sum, double total_sum, uint64_t n, uint32_t* avg,
+                        uint32_t* delta);
+
+/* ---- context ---- */
+int grb_create(const grb_params* p, grb_ctx** out);
+void grb_destroy(grb_ctx* ctx);
+const char* grb_last_error(const grb_ctx* ctx); /* ctx may be NULL: message of a failed grb_create */
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+uint64_t grb_launch_count(const grb_ctx* ctx);
+
+/* ---- K1: FASTQ decode + Phred sums into the device read store ----
+ * replaces btllib::SeqReader (goldrush_path.cpp:87,246; read_hashing.cpp:89-90; ntcard.hpp:200)
+ * and the summation loop of calc_phred_average (calc_phred_average.cpp:15-30). */
+typedef struct grb_read_meta
+{
+  uint64_t hdr_off;  /* byte offsets into the concatenation of everything ingested so far */
+  uint64_t seq_off;
+  uint64_t qual_off;
+  uint32_t hdr_len;  /* header line length without '@' and newline */
+  uint32_t len;      /* bases */
+  double phred_first_half_sum; /* running sum captured at i == n/2 - 1 (calc_phred_average.cpp:26-28) */
+  double phred_total_sum;
+  uint32_t non_acgt; /* 1 if the sequence holds a byte outside ACGTacgt (goldrush_path.cpp:293) */
+  uint32_t pad;
+} grb_read_meta;
+
+/* Decodes every complete 4-line record in bytes[0, n) and appends it to the read store.
+ * *consumed = bytes used; re-send the tail with the next chunk (final != 0: a last record without
+ * trailing newline is accepted).  bytes is HOST memory (pageable or pinned). */
+int grb_reads_ingest_fastq(grb_ctx* ctx, const char* bytes, size_t n, int final, size_t* consumed);
+uint64_t grb_reads_count(const grb_ctx* ctx);
+int grb_reads_get_meta(grb_ctx* ctx, uint64_t first, uint64_t count, grb_read_meta* out);
+/* per-read flags decided by the host from grb_read_meta (length / Phred / delta / ACGT / -f list) */
+#define GRB_READ_PASS1 1u /* hash whole read into the bit vector  (goldrush_path.cpp:302-305) */
+#define GRB_READ_PASS2 2u /* visit in the ordered selection loop  (goldrush_path.cpp:907-932) */
+int grb_reads_set_flags(grb_ctx* ctx, uint64_t first, uint64_t count, const uint8_t* flags);
+void grb_reads_clear(grb_ctx* ctx);
+/* one quality string: the two sums of calc_phred_average.cpp:15-30, computed on the device */
+int grb_phred_sums(grb_ctx* ctx, const char* qual, size_t n, double* first_half_sum,
+                   double* total_sum);
+
+/* ---- K5: ntCard-style estimate (ntcard.hpp:248-274 calc_ntcard_genome_size) ----
+ * Hashes every read in the store.  input_bytes = size of the FASTQ file (ntcard.hpp:180-183 picks
+ * sBits from it).  per_pattern may be NULL. */
+int grb_estimate_cardinality(grb_ctx* ctx, uint64_t input_bytes, uint64_t* per_pattern,
+                             uint64_t* total);
+
+/* ---- K2 + K4a/K4b: the bit vector (MIBFConstructSupport.hpp:66-84,134-147,165-181) ---- */
+int grb_filter_alloc(grb_ctx* ctx, uint64_t filter_bits);
+/* hashes every GRB_READ_PASS1 read whole and sets hash % filter_bits for each pattern */
+int grb_build_bitvector(grb_ctx* ctx);
+/* same for reads [first, first+count) only (multi-GPU sharding of pass 1) */
+int grb_build_bitvector_range(grb_ctx* ctx, uint64_t first, uint64_t count);
+/* rank build + allocation of the ID / count slots; *pop = number of set bits (= m_data length) */
+int grb_finalize_bitvector(grb_ctx* ctx, uint64_t* pop);
+/* silver-path rollover: reset_counts + reset_ID_vector (MIBFConstructSupport.hpp:183-186,
+ * MIBloomFilter.hpp:679-682) */
+int grb_reset_ids(grb_ctx* ctx);
+
+/* ---- K2 + K3 + K4c: the ordered selection loop (goldrush_path.cpp:892-1094, 1229-1256) ---- */
+typedef enum grb_verdict
+{
+  GRB_NOT_VISITED = 0, /* after exit(0) at path M+1, or never reached */
+  GRB_SKIPPED = 1,     /* too short / filtered (goldrush_path.cpp:907-932) */
+  GRB_UNTRIMMED = 2,   /* inserted whole, "_untrimmed" (:978-1011) */
+  GRB_TRIMMED = 3,     /* inserted tiles [trim_start, trim_end], "_trimmed" (:1035-1079) */
+  GRB_ASSIGNED = 4     /* dropped: fully assigned or bad flanks (:1013-1023, :1083-1088) */
+} grb_verdict;
+
+typedef struct grb_decision
+{
+  uint8_t verdict;     /* grb_verdict */
+  uint8_t pad[3];
+  uint32_t path;       /* 1-based silver path the record is written to (1 in golden mode) */
+  uint32_t trim_start; /* tiles, inclusive; valid for GRB_TRIMMED */
+  uint32_t trim_end;
+  uint32_t num_tiles;
+  uint32_t num_assigned;
+} grb_decision;
+
+/* counters of log_info_struct (goldrush_path.cpp:41-51), snapshot at each path rollover */
+typedef struct grb_path_stats
+{
+  uint64_t valid_reads;
+  uint64_t total_tiles;
+  uint64_t assigned_tiles;
+  uint64_t unassigned_tiles;
+  uint64_t queries;
+  uint64_t hits;
+  uint64_t misses;
+  uint64_t num_reads_in_path;
+  uint64_t inserted_bases;
+  double phred_sum_in_path;
+} grb_path_stats;
+
+/* Runs the selection loop over reads [first, first+count) of the store IN ORDER, continuing from
+ * the state left by the previous call.  decisions[count].  *finished != 0 once the reference would
+ * have called exit(0) (goldrush_path.cpp:174-176).  stats: up to stats_cap snapshots appended at
+ * each rollover during this call (*n_stats). */
+int grb_select_reads(grb_ctx* ctx, uint64_t first, uint64_t count, grb_decision* decisions,
+                     grb_path_stats* stats, uint32_t stats_cap, uint32_t* n_stats, int* finished);
+/* running counters of the current (unfinished) path + loop state */
+int grb_select_state(grb_ctx* ctx, grb_path_stats* current, uint64_t* curr_path,
+                     uint32_t* ids_inserted);
+
+/* ---- parity / debug exports (used by tests; each names the reference routine it mirrors) ---- */
+/* multiLensfrHashIterator over one sequence (multiLensfrHashIterator.hpp:29-68):
+ * out[frame * hash_num + pattern], frames = n - k + 1, stale-tail semantics included. */
+int grb_hash_sequence(grb_ctx* ctx, const char* seq, size_t n, uint64_t* out);
+/* plain LSB-first bit vector, (filter_bits + 63) / 64 words (sdsl::bit_vector layout) */
+int grb_copy_bitvector(grb_ctx* ctx, uint64_t* words);
+int grb_load_bitvector(grb_ctx* ctx, const uint64_t* words); /* before grb_finalize_bitvector */
+/* rank_support_il<1>(pos): set bits in [0, pos); also the bit itself (MIBloomFilter.hpp:465-491) */
+int grb_rank(grb_ctx* ctx, const uint64_t* pos, size_t n, uint64_t* rank, uint8_t* bit);
+int grb_get_ids(grb_ctx* ctx, const uint64_t* rank, size_t n, uint32_t* ids, uint32_t* counts);
+int grb_set_ids(grb_ctx* ctx, const uint64_t* rank, size_t n, const uint32_t* ids,
+                const uint32_t* counts);
+/* per-tile vote of calc_num_assigned_tiles (goldrush_path.cpp:544-626) for one stored read:
+ * best_id/best_count = arg-max (ties -> smallest id); candidates = every (id,count) with count > 2,
+ * at most cand_cap per tile written to cand_ids/cand_counts[tile * cand_cap + j], n_cand[tile] =
+ * true number.  counters[3] += {queries, hits, misses}. */
+int grb_query_read(grb_ctx* ctx, uint64_t read_idx, uint32_t* best_id, uint32_t* best_count,
+                   uint32_t* n_cand, uint32_t* cand_ids, uint32_t* cand_counts, uint32_t cand_cap,
+                   uint64_t* counters);
+/* insertMIBF(miBF, hashes, start, end, id) for one stored read (MIBFConstructSupport.hpp:247-283) */
+int grb_insert_tiles(grb_ctx* ctx, uint64_t read_idx, uint32_t tile_start, uint32_t tile_end,
+                     uint32_t id);
+
+/* ---- multi-GPU plumbing (one process per GPU; collectives are issued by the caller, e.g.
+ * torch.distributed / NCCL, on the raw device pointers) ---- */
+int grb_bitvector_device(grb_ctx* ctx, void** dev_ptr, uint64_t* bytes);
+/* dst |= src on this context's stream, n 8-byte words, both DEVICE pointers */
+int grb_or_words(grb_ctx* ctx, void* dst, const void* src, uint64_t n_words);
+int grb_sync(grb_ctx* ctx);
+/* device timing of the last grb_build_bitvector / grb_select_reads / ingest call, milliseconds */
+double grb_last_device_ms(const grb_ctx* ctx);
+
+/* ---- whole stage: what goldrush_path.cpp main() does between option parsing and exit ----
+ * (goldrush_path.cpp:1096-1275).  fastq = the whole input file in host memory.  Writes
+ * <prefix>_N.fq / <prefix>.fa exactly as the reference.  log may be NULL (else a FILE*-like
+ * callback receives the stderr text). */
+typedef struct grb_run_options
+{
+  grb_params params;       /* seeds may be NULL: derived from seed_preset */
+  const char* seed_preset; /* -s */
+  const char* prefix;      /* -p */
+  const char* filter_file; /* -f, may be NULL */
+  const char* input_path;  /* -i, used for messages and (if fastq == NULL) read from disk */
+  int32_t ntcard;          /* --ntcard */
+  int32_t verbose;         /* --verbose */
+  int32_t debug;           /* --debug */
+  int32_t write_outputs;   /* 0: decide only (bench) */
+} grb_run_options;
+
+typedef struct grb_run_result
+{
+  uint64_t num_reads;
+  uint64_t num_passed_reads;  /* pass 1 */
+  uint64_t bases_pass1;       /* bases hashed into the bit vector */
+  uint64_t reads_visited;     /* pass 2: reads that reached the query */
+  uint64_t bases_pass2;       /* sum of num_tiles * tile_length over visited reads */
+  uint64_t reads_selected;    /* untrimmed + trimmed */
+  uint64_t bases_selected;
+  uint64_t filter_bits;
+  uint64_t pop;
+  uint32_t phred_min;
+  uint32_t paths;             /* silver paths completed or in progress */
+  double ms_ingest;           /* device time per phase (CUDA events) */
+  double ms_pass1;
+  double ms_rank;
+  double ms_pass2;
+  double ms_wall;             /* host wall clock of the whole call */
+  uint64_t launches;
+  uint64_t out_digest;        /* FNV-1a over the bytes the output files hold (also when not written) */
+} grb_run_result;
+
+int grb_run_path(const grb_run_options* opt, const char* fastq, size_t fastq_len,
+                 grb_run_result* result, char* err, size_t err_cap);
+
+/* ---- synthetic reads; host only, used by bench.py and the tests ---- */
+typedef struct grb_synth_params
+{
+  uint64_t genome_len;
+  uint64_t seed;
+  double coverage;
+  uint32_t read_len; /* 0 = log-normal lengths with N50 = n50 */
+  uint32_t n50;
+  double sub_rate, ins_rate, del_rate;
+  uint32_t qmin, qmax; /* per-read base quality ~ UniformInt[qmin, qmax) */
+} grb_synth_params;
+
+uint64_t grb_synth_num_reads(const grb_synth_params* p);
+char* grb_synth_fastq(const grb_synth_params* p, uint64_t first, uint64_t count,
+                      uint64_t* out_len);
+void grb_free_host(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOLDRUSH_B200_H */
