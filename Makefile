@@ -1,0 +1,48 @@
+# Non-meson build of goldrush-b200 (meson is not installed in the build image; the meson.build
+# files next to the sources describe the same targets for a reference checkout).
+#
+#   make            libgoldrush_b200.so (CUDA, sm_100a) + goldrush-path + grb-synth
+#   make oracle     CPU checkers under oracle/ (test infrastructure)
+#   make host-tools grb-synth only (no CUDA needed)
+ROOT    := $(dir $(abspath $(lastword $(MAKEFILE_LIST))))
+# The image exports CXX=/opt/gcc/bin/g++ (no libgomp.spec there), so do not inherit $$CXX.
+GRB_CXX ?= $(firstword $(wildcard /usr/bin/g++) g++)
+NVCC    ?= $(firstword $(wildcard /usr/local/cuda/bin/nvcc) nvcc)
+CXXFLAGS_HOST := -std=c++17 -O2 -fopenmp -Wall -I$(ROOT)include
+NVCCFLAGS := -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
+             -Xcompiler -fPIC,-fopenmp,-Wall -I$(ROOT)include -I$(ROOT)goldrush_b200/csrc
+
+LIBDIR := $(ROOT)goldrush_b200/_lib
+LIB    := $(LIBDIR)/libgoldrush_b200.so
+CU_SRC := $(wildcard $(ROOT)goldrush_b200/csrc/*.cu)
+CU_HDR := $(wildcard $(ROOT)goldrush_b200/csrc/*.cuh) $(wildcard $(ROOT)goldrush_b200/csrc/*.h) $(ROOT)include/goldrush_b200.h
+HOST_LIB_SRC := $(ROOT)goldrush_b200/host/synth.cpp $(ROOT)goldrush_b200/host/host_util.cpp $(ROOT)goldrush_b200/host/path_driver.cpp $(ROOT)goldrush_b200/host/decide_host.cpp
+
+all: lib goldrush-path host-tools
+
+lib: $(LIB)
+
+$(LIB): $(CU_SRC) $(CU_HDR) $(HOST_LIB_SRC)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVCCFLAGS) -ccbin $(GRB_CXX) -shared -o $@ $(CU_SRC) $(HOST_LIB_SRC) -lcudart -lgomp
+
+goldrush-path: $(ROOT)build/goldrush-path
+
+$(ROOT)build/goldrush-path: $(ROOT)goldrush_b200/host/goldrush_path_main.cpp $(ROOT)goldrush_b200/host/opt.cpp $(LIB)
+	@mkdir -p $(ROOT)build
+	$(GRB_CXX) $(CXXFLAGS_HOST) -o $@ $(ROOT)goldrush_b200/host/goldrush_path_main.cpp $(ROOT)goldrush_b200/host/opt.cpp \
+	  -L$(LIBDIR) -lgoldrush_b200 -Wl,-rpath,'$$ORIGIN/../goldrush_b200/_lib'
+
+host-tools: $(ROOT)build/grb-synth
+
+$(ROOT)build/grb-synth: $(ROOT)goldrush_b200/host/synth.cpp $(ROOT)goldrush_b200/host/grb_synth_main.cpp $(ROOT)include/goldrush_b200.h
+	@mkdir -p $(ROOT)build
+	$(GRB_CXX) $(CXXFLAGS_HOST) -o $@ $(ROOT)goldrush_b200/host/synth.cpp $(ROOT)goldrush_b200/host/grb_synth_main.cpp
+
+oracle:
+	$(MAKE) -C $(ROOT)oracle all
+
+clean:
+	rm -rf $(ROOT)build $(LIBDIR)
+
+.PHONY: all lib goldrush-path host-tools oracle clean

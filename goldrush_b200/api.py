@@ -1,0 +1,428 @@
+"""ctypes mirror of include/goldrush_b200.h (same names, same argument meaning, errors -> GrbError)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path():
+    return os.path.join(_HERE, "_lib", "libgoldrush_b200.so")
+
+
+class GrbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"goldrush_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    """grb_params (opt:: globals, goldrush_path/opt.hpp:9-38)."""
+    _fields_ = [
+        ("assigned_max", C.c_uint64), ("unassigned_min", C.c_uint64), ("tile_length", C.c_uint64),
+        ("block_size", C.c_uint64), ("hash_universe", C.c_uint64), ("genome_size", C.c_uint64),
+        ("kmer_size", C.c_uint64), ("weight", C.c_uint64), ("min_length", C.c_uint64),
+        ("hash_num", C.c_uint64), ("occupancy", C.c_double), ("ratio", C.c_double),
+        ("max_paths", C.c_uint64), ("threshold", C.c_uint64), ("phred_min", C.c_uint32),
+        ("phred_delta", C.c_uint32), ("silver_path", C.c_int32), ("device", C.c_int32),
+        ("seeds", C.POINTER(C.c_char_p)),
+    ]
+
+
+class ReadMeta(C.Structure):
+    _fields_ = [
+        ("hdr_off", C.c_uint64), ("seq_off", C.c_uint64), ("qual_off", C.c_uint64),
+        ("hdr_len", C.c_uint32), ("len", C.c_uint32), ("phred_first_half_sum", C.c_double),
+        ("phred_total_sum", C.c_double), ("non_acgt", C.c_uint32), ("qual_len", C.c_uint32),
+    ]
+
+
+class Decision(C.Structure):
+    _fields_ = [
+        ("verdict", C.c_uint8), ("pad", C.c_uint8 * 3), ("path", C.c_uint32),
+        ("trim_start", C.c_uint32), ("trim_end", C.c_uint32), ("num_tiles", C.c_uint32),
+        ("num_assigned", C.c_uint32),
+    ]
+
+
+class PathStats(C.Structure):
+    _fields_ = [
+        ("valid_reads", C.c_uint64), ("total_tiles", C.c_uint64), ("assigned_tiles", C.c_uint64),
+        ("unassigned_tiles", C.c_uint64), ("queries", C.c_uint64), ("hits", C.c_uint64),
+        ("misses", C.c_uint64), ("num_reads_in_path", C.c_uint64), ("inserted_bases", C.c_uint64),
+        ("rollover_read", C.c_uint64), ("phred_sum_in_path", C.c_double),
+    ]
+
+
+class RunOptions(C.Structure):
+    _fields_ = [
+        ("params", Params), ("seed_preset", C.c_char_p), ("prefix", C.c_char_p),
+        ("filter_file", C.c_char_p), ("input_path", C.c_char_p), ("ntcard", C.c_int32),
+        ("verbose", C.c_int32), ("debug", C.c_int32), ("write_outputs", C.c_int32),
+        ("quiet", C.c_int32), ("jobs", C.c_int32),
+    ]
+
+
+class RunResult(C.Structure):
+    _fields_ = [
+        ("num_reads", C.c_uint64), ("num_passed_reads", C.c_uint64), ("bases_pass1", C.c_uint64),
+        ("reads_visited", C.c_uint64), ("bases_pass2", C.c_uint64), ("reads_selected", C.c_uint64),
+        ("bases_selected", C.c_uint64), ("filter_bits", C.c_uint64), ("pop", C.c_uint64),
+        ("phred_min", C.c_uint32), ("paths", C.c_uint32), ("ms_ingest", C.c_double),
+        ("ms_pass1", C.c_double), ("ms_rank", C.c_double), ("ms_pass2", C.c_double),
+        ("ms_wall", C.c_double), ("launches", C.c_uint64), ("out_digest", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class SynthParams(C.Structure):
+    _fields_ = [
+        ("genome_len", C.c_uint64), ("seed", C.c_uint64), ("coverage", C.c_double),
+        ("read_len", C.c_uint32), ("n50", C.c_uint32), ("sub_rate", C.c_double),
+        ("ins_rate", C.c_double), ("del_rate", C.c_double), ("qmin", C.c_uint32),
+        ("qmax", C.c_uint32),
+    ]
+
+
+VERDICTS = {0: "not_visited", 1: "skipped", 2: "untrimmed", 3: "trimmed", 4: "assigned"}
+READ_PASS1, READ_PASS2 = 1, 2
+
+_lib = None
+
+
+def lib():
+    """Loads libgoldrush_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise GrbError(-2, f"{path} is missing: run `make lib` (or __graft_entry__.build())")
+    L = C.CDLL(path)
+    u64, u32, i32, sz, dbl, vp = C.c_uint64, C.c_uint32, C.c_int, C.c_size_t, C.c_double, C.c_void_p
+    P = C.POINTER
+    sigs = {
+        "grb_params_default": (None, [P(Params)]),
+        "grb_make_seed_pattern": (i32, [C.c_char_p, C.c_uint, C.c_uint, C.c_uint, P(C.c_char_p)]),
+        "grb_calc_optimal_size": (u64, [u64, C.c_uint, dbl]),
+        "grb_default_hash_universe": (u64, [u64, u64, u64]),
+        "grb_phred_finalize": (None, [dbl, dbl, u64, P(u32), P(u32)]),
+        "grb_create": (i32, [P(Params), P(vp)]),
+        "grb_destroy": (None, [vp]),
+        "grb_last_error": (C.c_char_p, [vp]),
+        "grb_launch_count": (u64, [vp]),
+        "grb_reads_ingest_fastq": (i32, [vp, C.c_char_p, sz, i32, P(sz)]),
+        "grb_reads_count": (u64, [vp]),
+        "grb_reads_get_meta": (i32, [vp, u64, u64, P(ReadMeta)]),
+        "grb_reads_set_flags": (i32, [vp, u64, u64, vp]),
+        "grb_reads_clear": (None, [vp]),
+        "grb_phred_sums": (i32, [vp, C.c_char_p, sz, P(dbl), P(dbl)]),
+        "grb_estimate_cardinality": (i32, [vp, u64, P(u64), P(u64)]),
+        "grb_filter_alloc": (i32, [vp, u64]),
+        "grb_build_bitvector": (i32, [vp]),
+        "grb_build_bitvector_range": (i32, [vp, u64, u64]),
+        "grb_finalize_bitvector": (i32, [vp, P(u64)]),
+        "grb_reset_ids": (i32, [vp]),
+        "grb_select_reads": (i32, [vp, u64, u64, P(Decision), P(PathStats), u32, P(u32), P(i32)]),
+        "grb_select_state": (i32, [vp, P(PathStats), P(u64), P(u32)]),
+        "grb_hash_sequence": (i32, [vp, C.c_char_p, sz, vp]),
+        "grb_copy_bitvector": (i32, [vp, vp]),
+        "grb_load_bitvector": (i32, [vp, vp]),
+        "grb_rank": (i32, [vp, vp, sz, vp, vp]),
+        "grb_get_ids": (i32, [vp, vp, sz, vp, vp]),
+        "grb_set_ids": (i32, [vp, vp, sz, vp, vp]),
+        "grb_query_read": (i32, [vp, u64, vp, vp, vp, vp, vp, u32, vp]),
+        "grb_insert_tiles": (i32, [vp, u64, u32, u32, u32]),
+        "grb_bitvector_device": (i32, [vp, P(vp), P(u64)]),
+        "grb_or_words": (i32, [vp, vp, vp, u64]),
+        "grb_sync": (i32, [vp]),
+        "grb_last_device_ms": (dbl, [vp]),
+        "grb_run_path": (i32, [P(RunOptions), C.c_char_p, sz, P(RunResult), C.c_char_p, sz]),
+        "grb_synth_num_reads": (u64, [P(SynthParams)]),
+        "grb_synth_fastq": (vp, [P(SynthParams), u64, u64, P(u64)]),
+        "grb_free_host": (None, [vp]),
+        "grb_test_decide_host": (i32, [u32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u64, u64, u64,
+                                       P(u32), vp, vp, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._grb_symbols = sorted(sigs)
+    _lib = L
+    return L
+
+
+# ---- host-side scalar helpers -------------------------------------------------------------------
+def make_seed_pattern(preset, k, weight, h):
+    """spaced_seeds.cpp:7-68"""
+    bufs = [C.create_string_buffer(k + h + 2) for _ in range(h)]
+    arr = (C.c_char_p * h)(*[C.cast(b, C.c_char_p) for b in bufs])
+    rc = lib().grb_make_seed_pattern((preset or "").encode(), k, weight, h, arr)
+    if rc:
+        raise GrbError(rc, "cannot design a spaced seed for this k / w")
+    return [b.value.decode() for b in bufs]
+
+
+def calc_optimal_size(entries, hash_num, occupancy):
+    return lib().grb_calc_optimal_size(entries, hash_num, occupancy)
+
+
+def default_hash_universe(weight, genome_size, hash_num):
+    return lib().grb_default_hash_universe(weight, genome_size, hash_num)
+
+
+def phred_finalize(first_half_sum, total_sum, n):
+    a, d = C.c_uint32(), C.c_uint32()
+    lib().grb_phred_finalize(first_half_sum, total_sum, n, C.byref(a), C.byref(d))
+    return a.value, d.value
+
+
+def default_params(**kw):
+    p = Params()
+    lib().grb_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One grb_ctx.  Method names follow the C ABI without the grb_ prefix."""
+
+    def __init__(self, seeds, device=0, **params):
+        self._L = lib()
+        self.seeds = list(seeds)
+        p = default_params(**params)
+        p.hash_num = len(self.seeds)
+        p.kmer_size = params.get("kmer_size", len(self.seeds[0]))
+        p.device = device
+        self._seed_arr = (C.c_char_p * len(self.seeds))(*[s.encode() for s in self.seeds])
+        p.seeds = C.cast(self._seed_arr, C.POINTER(C.c_char_p))
+        self.params = p
+        h = C.c_void_p()
+        rc = self._L.grb_create(C.byref(p), C.byref(h))
+        if rc:
+            raise GrbError(rc, self._L.grb_last_error(None).decode())
+        self._h = h
+        self.h = len(self.seeds)
+        self.k = len(self.seeds[0])
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.grb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc:
+            raise GrbError(rc, self._L.grb_last_error(self._h).decode())
+
+    # K1
+    def reads_ingest_fastq(self, data: bytes, final=True):
+        used = C.c_size_t()
+        self._chk(self._L.grb_reads_ingest_fastq(self._h, data, len(data), int(final), C.byref(used)))
+        return used.value
+
+    def reads_count(self):
+        return self._L.grb_reads_count(self._h)
+
+    def reads_get_meta(self, first=0, count=None):
+        if count is None:
+            count = self.reads_count() - first
+        arr = (ReadMeta * max(1, count))()
+        if count:
+            self._chk(self._L.grb_reads_get_meta(self._h, first, count, arr))
+        return list(arr)[:count]
+
+    def reads_set_flags(self, flags, first=0):
+        f = np.ascontiguousarray(flags, dtype=np.uint8)
+        self._chk(self._L.grb_reads_set_flags(self._h, first, len(f), _ptr(f)))
+
+    def reads_clear(self):
+        self._L.grb_reads_clear(self._h)
+
+    def phred_sums(self, qual: bytes):
+        a, b = C.c_double(), C.c_double()
+        self._chk(self._L.grb_phred_sums(self._h, qual, len(qual), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # K5
+    def estimate_cardinality(self, input_bytes):
+        per = (C.c_uint64 * self.h)()
+        tot = C.c_uint64()
+        self._chk(self._L.grb_estimate_cardinality(self._h, input_bytes, per, C.byref(tot)))
+        return list(per), tot.value
+
+    # filter
+    def filter_alloc(self, bits):
+        self._chk(self._L.grb_filter_alloc(self._h, bits))
+        self.filter_bits = bits
+
+    def build_bitvector(self, first=None, count=None):
+        if first is None:
+            self._chk(self._L.grb_build_bitvector(self._h))
+        else:
+            self._chk(self._L.grb_build_bitvector_range(self._h, first, count))
+
+    def finalize_bitvector(self):
+        pop = C.c_uint64()
+        self._chk(self._L.grb_finalize_bitvector(self._h, C.byref(pop)))
+        self.pop = pop.value
+        return pop.value
+
+    def reset_ids(self):
+        self._chk(self._L.grb_reset_ids(self._h))
+
+    def copy_bitvector(self):
+        w = np.zeros((self.filter_bits + 63) // 64, dtype=np.uint64)
+        self._chk(self._L.grb_copy_bitvector(self._h, _ptr(w)))
+        return w
+
+    def load_bitvector(self, words):
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        self._chk(self._L.grb_load_bitvector(self._h, _ptr(w)))
+
+    def rank(self, pos):
+        pos = np.ascontiguousarray(pos, dtype=np.uint64)
+        r = np.zeros(len(pos), dtype=np.uint64)
+        b = np.zeros(len(pos), dtype=np.uint8)
+        self._chk(self._L.grb_rank(self._h, _ptr(pos), len(pos), _ptr(r), _ptr(b)))
+        return r, b
+
+    def get_ids(self, rank):
+        rank = np.ascontiguousarray(rank, dtype=np.uint64)
+        i = np.zeros(len(rank), dtype=np.uint32)
+        c = np.zeros(len(rank), dtype=np.uint32)
+        self._chk(self._L.grb_get_ids(self._h, _ptr(rank), len(rank), _ptr(i), _ptr(c)))
+        return i, c
+
+    def set_ids(self, rank, ids, counts):
+        rank = np.ascontiguousarray(rank, dtype=np.uint64)
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        self._chk(self._L.grb_set_ids(self._h, _ptr(rank), len(rank), _ptr(ids), _ptr(counts)))
+
+    def hash_sequence(self, seq: bytes):
+        frames = len(seq) - self.k + 1
+        out = np.zeros(max(0, frames) * self.h, dtype=np.uint64)
+        self._chk(self._L.grb_hash_sequence(self._h, seq, len(seq), _ptr(out)))
+        return out.reshape(frames, self.h)
+
+    # selection loop
+    def query_read(self, read_idx, num_tiles, cand_cap=64):
+        bi = np.zeros(max(1, num_tiles), dtype=np.uint32)
+        bc = np.zeros(max(1, num_tiles), dtype=np.uint32)
+        nc = np.zeros(max(1, num_tiles), dtype=np.uint32)
+        ci = np.zeros(max(1, num_tiles) * cand_cap, dtype=np.uint32)
+        cc = np.zeros(max(1, num_tiles) * cand_cap, dtype=np.uint32)
+        cnt = np.zeros(3, dtype=np.uint64)
+        self._chk(self._L.grb_query_read(self._h, read_idx, _ptr(bi), _ptr(bc), _ptr(nc), _ptr(ci),
+                                         _ptr(cc), cand_cap, _ptr(cnt)))
+        return (bi[:num_tiles], bc[:num_tiles], nc[:num_tiles],
+                ci.reshape(-1, cand_cap)[:num_tiles], cc.reshape(-1, cand_cap)[:num_tiles], cnt)
+
+    def insert_tiles(self, read_idx, tile_start, tile_end, id_):
+        self._chk(self._L.grb_insert_tiles(self._h, read_idx, tile_start, tile_end, id_))
+
+    def select_reads(self, first=0, count=None, stats_cap=64):
+        if count is None:
+            count = self.reads_count() - first
+        dec = (Decision * max(1, count))()
+        st = (PathStats * stats_cap)()
+        ns = C.c_uint32()
+        fin = C.c_int()
+        self._chk(self._L.grb_select_reads(self._h, first, count, dec, st, stats_cap, C.byref(ns),
+                                           C.byref(fin)))
+        return list(dec)[:count], list(st)[:ns.value], bool(fin.value)
+
+    def select_state(self):
+        st = PathStats()
+        cp = C.c_uint64()
+        ids = C.c_uint32()
+        self._chk(self._L.grb_select_state(self._h, C.byref(st), C.byref(cp), C.byref(ids)))
+        return st, cp.value, ids.value
+
+    # plumbing
+    def bitvector_device(self):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._chk(self._L.grb_bitvector_device(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def or_words(self, dst_ptr, src_ptr, n_words):
+        self._chk(self._L.grb_or_words(self._h, dst_ptr, src_ptr, n_words))
+
+    def sync(self):
+        self._chk(self._L.grb_sync(self._h))
+
+    def last_device_ms(self):
+        return self._L.grb_last_device_ms(self._h)
+
+    def launch_count(self):
+        return self._L.grb_launch_count(self._h)
+
+
+def run_path(fastq: bytes = None, input_path=None, prefix="goldrush_out", seed_preset="",
+             filter_file=None, ntcard=False, verbose=False, write_outputs=True, quiet=True,
+             device=0, **params):
+    """grb_run_path: the whole GoldRush-Path stage (goldrush_path.cpp main())."""
+    L = lib()
+    o = RunOptions()
+    o.params = default_params(**params)
+    o.params.device = device
+    o.seed_preset = (seed_preset or "").encode()
+    o.prefix = prefix.encode()
+    o.filter_file = filter_file.encode() if filter_file else None
+    o.input_path = input_path.encode() if input_path else None
+    o.ntcard = int(ntcard)
+    o.verbose = int(verbose)
+    o.write_outputs = int(write_outputs)
+    o.quiet = int(quiet)
+    res = RunResult()
+    err = C.create_string_buffer(1024)
+    rc = L.grb_run_path(C.byref(o), fastq, len(fastq) if fastq is not None else 0, C.byref(res),
+                        err, len(err))
+    if rc:
+        raise GrbError(rc, err.value.decode())
+    return res
+
+
+# ---- synthetic reads ------------------------------------------------------------------------------
+def synth_params(genome_len, coverage, read_len, seed, err=0.01, n50=20000, qmin=12, qmax=30):
+    return SynthParams(genome_len, seed, coverage, read_len, n50, err, err, err, qmin, qmax)
+
+
+def synth_num_reads(sp):
+    return lib().grb_synth_num_reads(C.byref(sp))
+
+
+def synth_fastq(sp, first=0, count=None) -> bytes:
+    L = lib()
+    if count is None:
+        count = L.grb_synth_num_reads(C.byref(sp)) - first
+    n = C.c_uint64()
+    p = L.grb_synth_fastq(C.byref(sp), first, count, C.byref(n))
+    if not p:
+        raise MemoryError("grb_synth_fastq")
+    try:
+        return C.string_at(p, n.value)
+    finally:
+        L.grb_free_host(p)

@@ -1,0 +1,1190 @@
+// libgoldrush_b200 — context, device memory management and the C ABI (include/goldrush_b200.h)
+// over the kernels in kernels_*.cuh.  One context = one CUDA device, one stream, one host thread.
+#include "common.cuh"
+#include "kernels_decode.cuh"
+#include "kernels_filter.cuh"
+#include "kernels_ntcard.cuh"
+#include "kernels_select.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+thread_local std::string g_create_error;
+const uint64_t kSeedBase[4] = { 0x3c8bfbb395c60474ULL, 0x3193c18562a02b4cULL,
+                                0x20323ed082572324ULL, 0x295549f54be24456ULL };
+}
+
+struct grb_ctx
+{
+  grb_params p{};
+  std::vector<std::string> seeds;
+  std::string err;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double last_ms = 0;
+  uint64_t launches = 0;
+  int sm_count = 148;
+
+  GrbSeedTables h_seed{};
+  GrbSeedTables* d_seed = nullptr;
+
+  // ---- read store ----
+  uint64_t n_reads = 0;
+  uint64_t n_words = 0;       // packed words in use
+  uint64_t ingested_bytes = 0; // running offset of the concatenated input
+  std::vector<uint32_t> h_len;
+  std::vector<uint64_t> h_word_off;
+  std::vector<uint8_t> h_flags;
+  std::vector<grb_read_meta> h_meta;
+  DevBuf<uint64_t> d_bases;
+  DevBuf<uint32_t> d_nmask;
+  DevBuf<uint64_t> d_word_off;
+  DevBuf<uint32_t> d_len;
+  DevBuf<uint8_t> d_flags;
+  bool flags_dirty = false;
+  // ingest scratch
+  DevBuf<uint8_t> d_raw;
+  DevBuf<uint32_t> d_blk_cnt;
+  DevBuf<uint64_t> d_blk_off;
+  DevBuf<uint32_t> d_nl;
+  DevBuf<grb_read_meta> d_meta;
+  DevBuf<uint32_t> d_wpr;
+  DevBuf<uint64_t> d_wpr_off;
+  DevBuf<uint32_t> d_err;
+
+  // ---- filter ----
+  GrbFilterDev filt{};
+  bool filter_alloc = false, finalized = false;
+  DevBuf<uint32_t> d_chunk_read;
+  DevBuf<uint64_t> d_chunk_first;
+
+  // ---- selection loop ----
+  GrbSelParams prm{};
+  GrbSelScratch sc{};
+  GrbSelState* d_state = nullptr;
+  bool sel_init = false;
+  bool sel_finished = false;
+  uint64_t sc_tiles = 0; // capacity of the per-read scratch, in tiles
+  uint64_t sc_tab = 0;   // capacity of the insert table, entries
+  DevBuf<uint64_t> b_stash;
+  DevBuf<uint32_t> b_best_id, b_best_count, b_n_cand, b_cand_id, b_cand_cnt, b_tile_id, b_snap;
+  DevBuf<uint8_t> b_tile_as;
+  DevBuf<GrbReadPlan> b_plan;
+  DevBuf<uint64_t> b_tab_key, b_tab_mask;
+  DevBuf<grb_decision> d_dec;
+  size_t query_smem = 0;
+
+  int fail(int code, const std::string& msg)
+  {
+    err = msg;
+    return code;
+  }
+  GrbReadsDev reads_dev() const
+  {
+    return GrbReadsDev{ d_bases.p, d_nmask.p, d_word_off.p, d_len.p, d_flags.p };
+  }
+  void tic() { cudaEventRecord(ev0, stream); }
+  void toc()
+  {
+    cudaEventRecord(ev1, stream);
+    cudaEventSynchronize(ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    last_ms = ms;
+  }
+};
+
+namespace {
+
+int
+build_seed_tables(grb_ctx* c)
+{
+  const auto& s = c->seeds;
+  const std::string& p0 = s[0];
+  if (p0.size() % 2 != 0 || p0.empty()) {
+    return c->fail(GRB_ERR_ARG, "seed pattern 0 must have even length (left + right halves)");
+  }
+  const size_t half = p0.size() / 2;
+  for (size_t i = 0; i < s.size(); ++i) {
+    if (s[i] != p0.substr(0, half) + std::string(i, '0') + p0.substr(half)) {
+      return c->fail(GRB_ERR_ARG, "seed patterns must be left + i zeros + right "
+                                  "(spaced_seeds.cpp:63-66)");
+    }
+    for (char ch : s[i]) {
+      if (ch != '0' && ch != '1') {
+        return c->fail(GRB_ERR_ARG, "seed pattern holds a character other than 0/1");
+      }
+    }
+  }
+  if (p0.size() + s.size() - 1 > GRB_MAX_SPAN || half > 32) {
+    return c->fail(GRB_ERR_ARG, "seed span + patterns - 1 exceeds 64 bases");
+  }
+  if (s.size() > GRB_MAX_PATTERNS) {
+    return c->fail(GRB_ERR_ARG, "more than 8 seed patterns");
+  }
+  GrbSeedTables& t = c->h_seed;
+  memset(&t, 0, sizeof t);
+  t.k = (uint32_t)p0.size();
+  t.h = (uint32_t)s.size();
+  t.half = (uint32_t)half;
+  for (size_t q = 0; q < p0.size(); ++q) {
+    if (p0[q] == '1') {
+      if (t.n_care >= GRB_MAX_WEIGHT) {
+        return c->fail(GRB_ERR_ARG, "seed weight exceeds 64");
+      }
+      const unsigned j = t.n_care++;
+      t.care[j] = (uint8_t)q;
+      if (q < half) {
+        t.n_left = t.n_care;
+      }
+      for (unsigned b = 0; b < 4; ++b) {
+        t.fwd[j][b] = grb_srol_any(kSeedBase[b], t.k - 1 - (unsigned)q);
+        t.rev[j][b] = grb_srol_any(kSeedBase[3 - b], (unsigned)q);
+      }
+    }
+  }
+  if (t.n_care == 0) {
+    return c->fail(GRB_ERR_ARG, "seed pattern has no care position");
+  }
+  return GRB_OK;
+}
+
+inline unsigned
+grid_for(uint64_t n, unsigned bs, unsigned cap)
+{
+  const uint64_t g = (n + bs - 1) / bs;
+  return (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(g, cap));
+}
+
+uint64_t
+next_pow2(uint64_t x)
+{
+  uint64_t p = 1;
+  while (p < x) {
+    p <<= 1;
+  }
+  return p;
+}
+
+} // namespace
+
+extern "C" {
+
+void
+grb_params_default(grb_params* p)
+{
+  memset(p, 0, sizeof *p);
+  p->assigned_max = 1;
+  p->unassigned_min = 5;
+  p->tile_length = 1000;
+  p->block_size = 10;
+  p->min_length = 20000;
+  p->hash_num = 3;
+  p->occupancy = 0.1;
+  p->ratio = 0.9;
+  p->max_paths = 1;
+  p->threshold = 10;
+  p->phred_min = 0;
+  p->phred_delta = 5;
+}
+
+const char*
+grb_last_error(const grb_ctx* ctx)
+{
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+uint64_t
+grb_launch_count(const grb_ctx* ctx)
+{
+  return ctx->launches;
+}
+
+double
+grb_last_device_ms(const grb_ctx* ctx)
+{
+  return ctx->last_ms;
+}
+
+int
+grb_create(const grb_params* p, grb_ctx** out)
+{
+  *out = nullptr;
+  grb_ctx* c = new grb_ctx;
+  auto bail = [&](int code, const std::string& m) {
+    g_create_error = m;
+    delete c;
+    return code;
+  };
+  c->p = *p;
+  if (!p->seeds || p->hash_num == 0) {
+    return bail(GRB_ERR_ARG, "grb_create: seeds / hash_num missing");
+  }
+  for (uint64_t i = 0; i < p->hash_num; ++i) {
+    c->seeds.emplace_back(p->seeds[i]);
+  }
+  c->p.seeds = nullptr;
+  if (p->tile_length == 0 || p->block_size == 0 || p->kmer_size == 0) {
+    return bail(GRB_ERR_ARG, "grb_create: tile_length, block_size and kmer_size must be non-zero");
+  }
+  int rc = build_seed_tables(c);
+  if (rc != GRB_OK) {
+    return bail(rc, c->err);
+  }
+  if (p->tile_length < c->h_seed.k + c->h_seed.h - 1) {
+    return bail(GRB_ERR_ARG, "grb_create: tile_length shorter than the longest seed span");
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    return bail(GRB_ERR_CUDA, std::string("no usable CUDA device: ") +
+                                (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  }
+  if (p->device < 0 || p->device >= ndev) {
+    return bail(GRB_ERR_ARG, "grb_create: device ordinal out of range");
+  }
+  c->device = p->device;
+  if ((e = cudaSetDevice(c->device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+    return bail(GRB_ERR_CUDA, std::string("CUDA init: ") + cudaGetErrorString(e));
+  }
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+  if ((e = cudaMalloc(&c->d_seed, sizeof(GrbSeedTables))) != cudaSuccess ||
+      (e = cudaMemcpy(c->d_seed, &c->h_seed, sizeof(GrbSeedTables), cudaMemcpyHostToDevice)) !=
+        cudaSuccess) {
+    return bail(GRB_ERR_CUDA, std::string("seed table upload: ") + cudaGetErrorString(e));
+  }
+  // 10^(-q/10) with glibc pow, indexed by the raw quality byte (calc_phred_average.cpp:17-20;
+  // `char` is signed on this platform, as in the reference build)
+  double tab[256];
+  for (int b = 0; b < 256; ++b) {
+    const int phred_score = (int)((char)b - 33);
+    tab[b] = pow(10.0, -phred_score / 10.0);
+  }
+  if ((e = cudaMemcpyToSymbol(c_delog, tab, sizeof tab)) != cudaSuccess) {
+    return bail(GRB_ERR_CUDA, std::string("phred table upload: ") + cudaGetErrorString(e));
+  }
+  *out = c;
+  return GRB_OK;
+}
+
+void
+grb_destroy(grb_ctx* c)
+{
+  if (!c) {
+    return;
+  }
+  cudaSetDevice(c->device);
+  if (c->stream) {
+    cudaStreamSynchronize(c->stream);
+  }
+  if (c->filt.blocks) {
+    cudaFree(c->filt.blocks);
+  }
+  if (c->filt.slots) {
+    cudaFree(c->filt.slots);
+  }
+  if (c->d_state) {
+    cudaFree(c->d_state);
+  }
+  if (c->d_seed) {
+    cudaFree(c->d_seed);
+  }
+  if (c->ev0) {
+    cudaEventDestroy(c->ev0);
+  }
+  if (c->ev1) {
+    cudaEventDestroy(c->ev1);
+  }
+  cudaStream_t s = c->stream;
+  delete c;
+  if (s) {
+    cudaStreamDestroy(s);
+  }
+}
+
+int
+grb_sync(grb_ctx* c)
+{
+  GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: ingest
+// ------------------------------------------------------------------------------------------
+uint64_t
+grb_reads_count(const grb_ctx* c)
+{
+  return c->n_reads;
+}
+
+void
+grb_reads_clear(grb_ctx* c)
+{
+  c->n_reads = 0;
+  c->n_words = 0;
+  c->ingested_bytes = 0;
+  c->h_len.clear();
+  c->h_word_off.clear();
+  c->h_flags.clear();
+  c->h_meta.clear();
+}
+
+int
+grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_t* consumed)
+{
+  cudaSetDevice(c->device);
+  *consumed = 0;
+  if (n == 0) {
+    return GRB_OK;
+  }
+  if (n > (1ull << 31)) {
+    return c->fail(GRB_ERR_ARG, "grb_reads_ingest_fastq: chunk larger than 2 GiB");
+  }
+  if (c->ingested_bytes == 0 && c->n_reads == 0 && bytes[0] != '@') {
+    return c->fail(GRB_ERR_FORMAT, "Gold Path requires fastq format");
+  }
+  cudaStream_t s = c->stream;
+  c->tic();
+  const uint64_t padded = (n + 4095) / 4096 * 4096;
+  const uint64_t n_blk = padded / 4096;
+  GRB_CUDA(c, c->d_raw.reserve(padded, 0, s));
+  GRB_CUDA(c, cudaMemsetAsync(c->d_raw.p + (padded - 4096), 0, 4096, s));
+  GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, bytes, n, cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, c->d_blk_cnt.reserve(n_blk, 0, s));
+  GRB_CUDA(c, c->d_blk_off.reserve(n_blk + 1, 0, s));
+  k_nl_count<<<(unsigned)n_blk, 256, 0, s>>>(c->d_raw.p, c->d_blk_cnt.p);
+  k_scan_u32<<<1, 1024, 0, s>>>(c->d_blk_cnt.p, c->d_blk_off.p, n_blk);
+  c->launches += 2;
+  uint64_t n_nl = 0;
+  GRB_CUDA(c, cudaMemcpyAsync(&n_nl, c->d_blk_off.p + n_blk, 8, cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  uint64_t n_lines = n_nl;
+  if (final && bytes[n - 1] != '\n') {
+    ++n_lines; // last line without a trailing newline
+  }
+  const uint64_t n_rec = n_lines / 4;
+  if (n_rec == 0) {
+    c->toc();
+    return GRB_OK;
+  }
+  GRB_CUDA(c, c->d_nl.reserve(n_nl + 1, 0, s));
+  k_nl_write<<<(unsigned)n_blk, 256, 0, s>>>(c->d_raw.p, c->d_blk_off.p, c->d_nl.p);
+  GRB_CUDA(c, c->d_meta.reserve(n_rec, 0, s));
+  GRB_CUDA(c, c->d_wpr.reserve(n_rec, 0, s));
+  GRB_CUDA(c, c->d_wpr_off.reserve(n_rec + 1, 0, s));
+  GRB_CUDA(c, c->d_err.reserve(1, 0, s));
+  GRB_CUDA(c, cudaMemsetAsync(c->d_err.p, 0, 4, s));
+  k_records<<<grid_for(n_rec, 128, 1u << 30), 128, 0, s>>>(c->d_raw.p, n, c->d_nl.p, n_nl, n_rec,
+                                                          c->ingested_bytes, c->d_meta.p,
+                                                          c->d_wpr.p, c->d_err.p);
+  k_scan_u32<<<1, 1024, 0, s>>>(c->d_wpr.p, c->d_wpr_off.p, n_rec);
+  c->launches += 3;
+  uint64_t new_words = 0;
+  uint32_t fmt_err = 0;
+  uint32_t last_nl = 0;
+  GRB_CUDA(c, cudaMemcpyAsync(&new_words, c->d_wpr_off.p + n_rec, 8, cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(c, cudaMemcpyAsync(&fmt_err, c->d_err.p, 4, cudaMemcpyDeviceToHost, s));
+  if (4 * n_rec - 1 < n_nl) {
+    GRB_CUDA(c, cudaMemcpyAsync(&last_nl, c->d_nl.p + (4 * n_rec - 1), 4, cudaMemcpyDeviceToHost, s));
+  }
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  if (fmt_err) {
+    return c->fail(GRB_ERR_FORMAT, "malformed FASTQ record (expected '@' header and '+' separator)");
+  }
+  // grow the store (+3 words so a 64-base window may read past the last read)
+  GRB_CUDA(c, c->d_bases.reserve(c->n_words + new_words + 4, c->n_words, s));
+  GRB_CUDA(c, c->d_nmask.reserve(c->n_words + new_words + 4, c->n_words, s));
+  GRB_CUDA(c, c->d_word_off.reserve(c->n_reads + n_rec, c->n_reads, s));
+  GRB_CUDA(c, c->d_len.reserve(c->n_reads + n_rec, c->n_reads, s));
+  GRB_CUDA(c, c->d_flags.reserve(c->n_reads + n_rec, c->n_reads, s));
+  k_pack<<<(unsigned)n_rec, 256, 0, s>>>(c->d_raw.p, c->ingested_bytes, c->d_meta.p,
+                                         c->d_wpr_off.p, c->n_words, c->d_bases.p, c->d_nmask.p);
+  GRB_CUDA(c, cudaMemsetAsync(c->d_bases.p + c->n_words + new_words, 0, 4 * 8, s));
+  k_phred<<<grid_for(n_rec, 64, 1u << 30), 64, 0, s>>>(c->d_raw.p, c->ingested_bytes, c->d_meta.p,
+                                                      n_rec);
+  c->launches += 2;
+  const size_t old = c->h_meta.size();
+  c->h_meta.resize(old + n_rec);
+  std::vector<uint64_t> woff(n_rec + 1);
+  GRB_CUDA(c, cudaMemcpyAsync(c->h_meta.data() + old, c->d_meta.p, n_rec * sizeof(grb_read_meta),
+                              cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(c, cudaMemcpyAsync(woff.data(), c->d_wpr_off.p, (n_rec + 1) * 8, cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  c->h_len.resize(old + n_rec);
+  c->h_word_off.resize(old + n_rec);
+  c->h_flags.resize(old + n_rec, 0);
+  for (uint64_t i = 0; i < n_rec; ++i) {
+    c->h_len[old + i] = c->h_meta[old + i].len;
+    c->h_word_off[old + i] = c->n_words + woff[i];
+    c->h_flags[old + i] = c->h_meta[old + i].non_acgt ? 4 : 0;
+  }
+  GRB_CUDA(c, cudaMemcpyAsync(c->d_word_off.p + old, c->h_word_off.data() + old, n_rec * 8,
+                              cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemcpyAsync(c->d_len.p + old, c->h_len.data() + old, n_rec * 4,
+                              cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemcpyAsync(c->d_flags.p + old, c->h_flags.data() + old, n_rec,
+                              cudaMemcpyHostToDevice, s));
+  c->toc();
+  GRB_CUDA(c, cudaGetLastError());
+  c->n_reads += n_rec;
+  c->n_words += new_words;
+  *consumed = (4 * n_rec - 1 < n_nl) ? (size_t)last_nl + 1 : n;
+  c->ingested_bytes += *consumed;
+  return GRB_OK;
+}
+
+int
+grb_reads_get_meta(grb_ctx* c, uint64_t first, uint64_t count, grb_read_meta* out)
+{
+  if (first + count > c->n_reads) {
+    return c->fail(GRB_ERR_ARG, "grb_reads_get_meta: range past the end of the read store");
+  }
+  memcpy(out, c->h_meta.data() + first, count * sizeof(grb_read_meta));
+  return GRB_OK;
+}
+
+int
+grb_reads_set_flags(grb_ctx* c, uint64_t first, uint64_t count, const uint8_t* flags)
+{
+  cudaSetDevice(c->device);
+  if (first + count > c->n_reads) {
+    return c->fail(GRB_ERR_ARG, "grb_reads_set_flags: range past the end of the read store");
+  }
+  for (uint64_t i = 0; i < count; ++i) {
+    c->h_flags[first + i] = (uint8_t)((c->h_flags[first + i] & 4u) | (flags[i] & 3u));
+  }
+  GRB_CUDA(c, cudaMemcpyAsync(c->d_flags.p + first, c->h_flags.data() + first, count,
+                              cudaMemcpyHostToDevice, c->stream));
+  GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GRB_OK;
+}
+
+int
+grb_phred_sums(grb_ctx* c, const char* qual, size_t n, double* first_half_sum, double* total_sum)
+{
+  cudaSetDevice(c->device);
+  cudaStream_t s = c->stream;
+  GRB_CUDA(c, c->d_raw.reserve(n + 16, 0, s));
+  GRB_CUDA(c, c->d_meta.reserve(1, 0, s));
+  grb_read_meta m{};
+  m.qual_off = 0;
+  m.qual_len = (uint32_t)n;
+  GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, qual, n, cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemcpyAsync(c->d_meta.p, &m, sizeof m, cudaMemcpyHostToDevice, s));
+  k_phred<<<1, 32, 0, s>>>(c->d_raw.p, 0, c->d_meta.p, 1);
+  c->launches += 1;
+  GRB_CUDA(c, cudaMemcpyAsync(&m, c->d_meta.p, sizeof m, cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  *first_half_sum = m.phred_first_half_sum;
+  *total_sum = m.phred_total_sum;
+  return GRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: ntcard
+// ------------------------------------------------------------------------------------------
+int
+grb_estimate_cardinality(grb_ctx* c, uint64_t input_bytes, uint64_t* per_pattern, uint64_t* total)
+{
+  cudaSetDevice(c->device);
+  cudaStream_t s = c->stream;
+  const unsigned rBits = 27;
+  const unsigned sBits = input_bytes < 50000000000ULL ? 7 : 11; // ntcard.hpp:182-183
+  const uint64_t rBuck = 1ull << rBits;
+  const unsigned h = c->h_seed.h;
+  for (uint64_t i = 0; i < c->n_reads; ++i) {
+    if (c->h_len[i] < c->h_seed.k + h - 1) {
+      return c->fail(GRB_ERR_ARG, "SeedNtHash: sequence length is smaller than k");
+    }
+  }
+  DevBuf<uint32_t> counters; // [h][2][rBuck], 32-bit so the uint16 wrap of ntcard.hpp:82,92 is exact
+  DevBuf<uint32_t> valid;    // [n_reads][h] valid windows of reads that hold non-ACGT bytes
+  DevBuf<unsigned long long> zeros;
+  GRB_CUDA(c, counters.reserve((size_t)h * 2 * rBuck, 0, s));
+  GRB_CUDA(c, valid.reserve(std::max<uint64_t>(1, c->n_reads * h), 0, s));
+  GRB_CUDA(c, zeros.reserve(h * 2, 0, s));
+  GRB_CUDA(c, cudaMemsetAsync(counters.p, 0, (size_t)h * 2 * rBuck * 4, s));
+  GRB_CUDA(c, cudaMemsetAsync(valid.p, 0, std::max<uint64_t>(1, c->n_reads * h) * 4, s));
+  GRB_CUDA(c, cudaMemsetAsync(zeros.p, 0, h * 2 * 8, s));
+  c->tic();
+  // chunk table over ALL reads (ntcard.hpp:203-205 hashes every record, unfiltered)
+  std::vector<uint32_t> chunk_read;
+  std::vector<uint64_t> chunk_first(c->n_reads);
+  for (uint64_t r = 0; r < c->n_reads; ++r) {
+    chunk_first[r] = chunk_read.size();
+    const uint64_t nc = ((uint64_t)c->h_len[r] + GRB_FILL_CHUNK - 1) / GRB_FILL_CHUNK;
+    chunk_read.insert(chunk_read.end(), nc, (uint32_t)r);
+  }
+  if (!chunk_read.empty()) {
+    GRB_CUDA(c, c->d_chunk_read.reserve(chunk_read.size(), 0, s));
+    GRB_CUDA(c, c->d_chunk_first.reserve(c->n_reads, 0, s));
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_chunk_read.p, chunk_read.data(), chunk_read.size() * 4,
+                                cudaMemcpyHostToDevice, s));
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_chunk_first.p, chunk_first.data(), c->n_reads * 8,
+                                cudaMemcpyHostToDevice, s));
+    k_ntcard_count<<<grid_for(chunk_read.size(), 1, c->sm_count * 8), 256, 0, s>>>(
+      c->reads_dev(), c->d_seed, c->d_chunk_read.p, c->d_chunk_first.p, chunk_read.size(),
+      counters.p, valid.p, sBits, rBits);
+    k_ntcard_tail<<<grid_for(c->n_reads * h, 128, 1u << 30), 128, 0, s>>>(
+      c->reads_dev(), c->d_seed, c->n_reads, counters.p, valid.p, sBits, rBits);
+    c->launches += 2;
+  }
+  k_ntcard_zeros<<<c->sm_count * 4, 256, 0, s>>>(counters.p, (uint64_t)h * 2, rBuck, zeros.p);
+  c->launches += 1;
+  std::vector<unsigned long long> hz(h * 2);
+  GRB_CUDA(c, cudaMemcpyAsync(hz.data(), zeros.p, h * 2 * 8, cudaMemcpyDeviceToHost, s));
+  c->toc();
+  GRB_CUDA(c, cudaGetLastError());
+  uint64_t sum = 0;
+  for (unsigned i = 0; i < h; ++i) { // ntcard.hpp:127-139 compEst, only F0 is consumed (:265-270)
+    const double pMean0 = ((double)hz[2 * i] + (double)hz[2 * i + 1]) / (1.0 * 2);
+    const double F0Mean =
+      (double)(ssize_t)((rBits * log(2) - log(pMean0)) * 1.0 * ((size_t)1 << (sBits + rBits)));
+    const uint64_t f0 = (uint64_t)(size_t)F0Mean;
+    if (per_pattern) {
+      per_pattern[i] = f0;
+    }
+    sum += f0;
+  }
+  *total = sum;
+  return GRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// filter
+// ------------------------------------------------------------------------------------------
+int
+grb_filter_alloc(grb_ctx* c, uint64_t filter_bits)
+{
+  cudaSetDevice(c->device);
+  if (filter_bits < 64) {
+    return c->fail(GRB_ERR_ARG, "grb_filter_alloc: filter smaller than 64 bits");
+  }
+  if (c->filt.blocks) {
+    cudaFree(c->filt.blocks);
+    c->filt.blocks = nullptr;
+  }
+  if (c->filt.slots) {
+    cudaFree(c->filt.slots);
+    c->filt.slots = nullptr;
+  }
+  c->filt.bits = filter_bits;
+  c->filt.inv = (uint64_t)((((__uint128_t)1) << 64) / filter_bits);
+  c->filt.n_blocks = (filter_bits + GRB_BLK_BITS - 1) / GRB_BLK_BITS;
+  c->filt.pop = 0;
+  GRB_CUDA(c, cudaMalloc(&c->filt.blocks, c->filt.n_blocks * 32));
+  GRB_CUDA(c, cudaMemsetAsync(c->filt.blocks, 0, c->filt.n_blocks * 32, c->stream));
+  c->filter_alloc = true;
+  c->finalized = false;
+  c->sel_init = false;
+  c->sel_finished = false;
+  return GRB_OK;
+}
+
+int
+grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
+{
+  cudaSetDevice(c->device);
+  if (!c->filter_alloc || c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_build_bitvector: needs grb_filter_alloc and no finalize yet");
+  }
+  if (first + count > c->n_reads) {
+    return c->fail(GRB_ERR_ARG, "grb_build_bitvector_range: range past the end of the read store");
+  }
+  cudaStream_t s = c->stream;
+  std::vector<uint32_t> chunk_read;
+  std::vector<uint64_t> chunk_first(c->n_reads, 0);
+  const uint32_t need = c->h_seed.k + c->h_seed.h - 1;
+  for (uint64_t r = first; r < first + count; ++r) {
+    if (!(c->h_flags[r] & GRB_READ_PASS1)) {
+      continue;
+    }
+    if (c->h_len[r] < need) { // btllib::SeedNtHash refuses sequences shorter than the seed
+      return c->fail(GRB_ERR_ARG, "SeedNtHash: sequence length is smaller than k");
+    }
+    if (c->h_flags[r] & 4u) {
+      return c->fail(GRB_ERR_ARG, "a read with non-ACGT bases is flagged GRB_READ_PASS1");
+    }
+    chunk_first[r] = chunk_read.size();
+    const uint64_t nc = ((uint64_t)c->h_len[r] + GRB_FILL_CHUNK - 1) / GRB_FILL_CHUNK;
+    chunk_read.insert(chunk_read.end(), nc, (uint32_t)r);
+  }
+  c->tic();
+  if (!chunk_read.empty()) {
+    GRB_CUDA(c, c->d_chunk_read.reserve(chunk_read.size(), 0, s));
+    GRB_CUDA(c, c->d_chunk_first.reserve(c->n_reads, 0, s));
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_chunk_read.p, chunk_read.data(), chunk_read.size() * 4,
+                                cudaMemcpyHostToDevice, s));
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_chunk_first.p, chunk_first.data(), c->n_reads * 8,
+                                cudaMemcpyHostToDevice, s));
+    c->tic();
+    k_fill_bits<<<grid_for(chunk_read.size(), 1, c->sm_count * 16), 256, 0, s>>>(
+      c->reads_dev(), c->d_seed, c->filt, c->d_chunk_read.p, c->d_chunk_first.p, chunk_read.size());
+    c->launches += 1;
+  }
+  c->toc();
+  GRB_CUDA(c, cudaGetLastError());
+  return GRB_OK;
+}
+
+int
+grb_build_bitvector(grb_ctx* c)
+{
+  return grb_build_bitvector_range(c, 0, c->n_reads);
+}
+
+int
+grb_finalize_bitvector(grb_ctx* c, uint64_t* pop)
+{
+  cudaSetDevice(c->device);
+  if (!c->filter_alloc || c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_finalize_bitvector: needs grb_filter_alloc, once");
+  }
+  cudaStream_t s = c->stream;
+  const uint64_t per_cta = 256ull * GRB_RANK_ITEMS;
+  const uint64_t n_cta = (c->filt.n_blocks + per_cta - 1) / per_cta;
+  DevBuf<uint32_t> partial;
+  DevBuf<uint64_t> partial_off;
+  GRB_CUDA(c, partial.reserve(n_cta, 0, s));
+  GRB_CUDA(c, partial_off.reserve(n_cta + 1, 0, s));
+  c->tic();
+  k_rank_partial<<<(unsigned)n_cta, 256, 0, s>>>(c->filt.blocks, c->filt.n_blocks, partial.p);
+  k_scan_u32<<<1, 1024, 0, s>>>(partial.p, partial_off.p, n_cta);
+  k_rank_write<<<(unsigned)n_cta, 256, 0, s>>>(c->filt.blocks, c->filt.n_blocks, partial_off.p);
+  c->launches += 3;
+  uint64_t total = 0;
+  GRB_CUDA(c, cudaMemcpyAsync(&total, partial_off.p + n_cta, 8, cudaMemcpyDeviceToHost, s));
+  c->toc();
+  GRB_CUDA(c, cudaGetLastError());
+  c->filt.pop = total;
+  // m_data + m_counts (MIBloomFilter.hpp:165-184, MIBFConstructSupport.hpp:175-181), zeroed
+  GRB_CUDA(c, cudaMalloc(&c->filt.slots, std::max<uint64_t>(1, total) * sizeof(uint2)));
+  GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, std::max<uint64_t>(1, total) * sizeof(uint2), s));
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  c->finalized = true;
+  if (pop) {
+    *pop = total;
+  }
+  return GRB_OK;
+}
+
+int
+grb_reset_ids(grb_ctx* c)
+{
+  cudaSetDevice(c->device);
+  if (!c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_reset_ids before grb_finalize_bitvector");
+  }
+  GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, std::max<uint64_t>(1, c->filt.pop) * sizeof(uint2),
+                              c->stream));
+  return GRB_OK;
+}
+
+int
+grb_bitvector_device(grb_ctx* c, void** dev_ptr, uint64_t* bytes)
+{
+  if (!c->filter_alloc) {
+    return c->fail(GRB_ERR_STATE, "grb_bitvector_device before grb_filter_alloc");
+  }
+  *dev_ptr = c->filt.blocks;
+  *bytes = c->filt.n_blocks * 32;
+  return GRB_OK;
+}
+
+int
+grb_or_words(grb_ctx* c, void* dst, const void* src, uint64_t n_words)
+{
+  cudaSetDevice(c->device);
+  k_or_words<<<grid_for(n_words, 256, c->sm_count * 8), 256, 0, c->stream>>>(
+    (uint64_t*)dst, (const uint64_t*)src, n_words);
+  c->launches += 1;
+  GRB_CUDA(c, cudaGetLastError());
+  return GRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// parity exports
+// ------------------------------------------------------------------------------------------
+int
+grb_copy_bitvector(grb_ctx* c, uint64_t* words)
+{
+  cudaSetDevice(c->device);
+  if (!c->filter_alloc) {
+    return c->fail(GRB_ERR_STATE, "grb_copy_bitvector before grb_filter_alloc");
+  }
+  const uint64_t n_words = (c->filt.bits + 63) / 64;
+  DevBuf<uint64_t> tmp;
+  GRB_CUDA(c, tmp.reserve(n_words, 0, c->stream));
+  k_export_plain<<<grid_for(n_words, 256, c->sm_count * 8), 256, 0, c->stream>>>(c->filt.blocks,
+                                                                                n_words, tmp.p);
+  c->launches += 1;
+  GRB_CUDA(c, cudaMemcpyAsync(words, tmp.p, n_words * 8, cudaMemcpyDeviceToHost, c->stream));
+  GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GRB_OK;
+}
+
+int
+grb_load_bitvector(grb_ctx* c, const uint64_t* words)
+{
+  cudaSetDevice(c->device);
+  if (!c->filter_alloc || c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_load_bitvector: needs grb_filter_alloc and no finalize yet");
+  }
+  const uint64_t n_words = (c->filt.bits + 63) / 64;
+  DevBuf<uint64_t> tmp;
+  GRB_CUDA(c, tmp.reserve(n_words, 0, c->stream));
+  GRB_CUDA(c, cudaMemcpyAsync(tmp.p, words, n_words * 8, cudaMemcpyHostToDevice, c->stream));
+  GRB_CUDA(c, cudaMemsetAsync(c->filt.blocks, 0, c->filt.n_blocks * 32, c->stream));
+  k_import_plain<<<grid_for(n_words, 256, c->sm_count * 8), 256, 0, c->stream>>>(c->filt.blocks,
+                                                                                n_words, tmp.p);
+  c->launches += 1;
+  GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  return GRB_OK;
+}
+
+int
+grb_rank(grb_ctx* c, const uint64_t* pos, size_t n, uint64_t* rank, uint8_t* bit)
+{
+  cudaSetDevice(c->device);
+  if (!c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_rank before grb_finalize_bitvector");
+  }
+  for (size_t i = 0; i < n; ++i) {
+    if (pos[i] >= c->filt.bits) {
+      return c->fail(GRB_ERR_ARG, "grb_rank: position past the end of the filter");
+    }
+  }
+  DevBuf<uint64_t> dpos, drank;
+  DevBuf<uint8_t> dbit;
+  cudaStream_t s = c->stream;
+  GRB_CUDA(c, dpos.reserve(n, 0, s));
+  GRB_CUDA(c, drank.reserve(n, 0, s));
+  GRB_CUDA(c, dbit.reserve(n, 0, s));
+  GRB_CUDA(c, cudaMemcpyAsync(dpos.p, pos, n * 8, cudaMemcpyHostToDevice, s));
+  k_rank_query<<<grid_for(n, 256, 1u << 30), 256, 0, s>>>(c->filt, dpos.p, n, drank.p, dbit.p);
+  c->launches += 1;
+  GRB_CUDA(c, cudaMemcpyAsync(rank, drank.p, n * 8, cudaMemcpyDeviceToHost, s));
+  if (bit) {
+    GRB_CUDA(c, cudaMemcpyAsync(bit, dbit.p, n, cudaMemcpyDeviceToHost, s));
+  }
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  return GRB_OK;
+}
+
+int
+grb_get_ids(grb_ctx* c, const uint64_t* rank, size_t n, uint32_t* ids, uint32_t* counts)
+{
+  cudaSetDevice(c->device);
+  if (!c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_get_ids before grb_finalize_bitvector");
+  }
+  for (size_t i = 0; i < n; ++i) {
+    if (rank[i] >= c->filt.pop) {
+      return c->fail(GRB_ERR_ARG, "grb_get_ids: rank past the end of the ID array");
+    }
+  }
+  DevBuf<uint64_t> dr;
+  DevBuf<uint32_t> di, dc;
+  cudaStream_t s = c->stream;
+  GRB_CUDA(c, dr.reserve(n, 0, s));
+  GRB_CUDA(c, di.reserve(n, 0, s));
+  GRB_CUDA(c, dc.reserve(n, 0, s));
+  GRB_CUDA(c, cudaMemcpyAsync(dr.p, rank, n * 8, cudaMemcpyHostToDevice, s));
+  k_get_slots<<<grid_for(n, 256, 1u << 30), 256, 0, s>>>(c->filt.slots, dr.p, n, di.p, dc.p);
+  c->launches += 1;
+  GRB_CUDA(c, cudaMemcpyAsync(ids, di.p, n * 4, cudaMemcpyDeviceToHost, s));
+  if (counts) {
+    GRB_CUDA(c, cudaMemcpyAsync(counts, dc.p, n * 4, cudaMemcpyDeviceToHost, s));
+  }
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  return GRB_OK;
+}
+
+int
+grb_set_ids(grb_ctx* c, const uint64_t* rank, size_t n, const uint32_t* ids, const uint32_t* counts)
+{
+  cudaSetDevice(c->device);
+  if (!c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_set_ids before grb_finalize_bitvector");
+  }
+  for (size_t i = 0; i < n; ++i) {
+    if (rank[i] >= c->filt.pop) {
+      return c->fail(GRB_ERR_ARG, "grb_set_ids: rank past the end of the ID array");
+    }
+  }
+  DevBuf<uint64_t> dr;
+  DevBuf<uint32_t> di, dc;
+  cudaStream_t s = c->stream;
+  GRB_CUDA(c, dr.reserve(n, 0, s));
+  GRB_CUDA(c, di.reserve(n, 0, s));
+  GRB_CUDA(c, dc.reserve(n, 0, s));
+  GRB_CUDA(c, cudaMemcpyAsync(dr.p, rank, n * 8, cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemcpyAsync(di.p, ids, n * 4, cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemcpyAsync(dc.p, counts, n * 4, cudaMemcpyHostToDevice, s));
+  k_set_slots<<<grid_for(n, 256, 1u << 30), 256, 0, s>>>(c->filt.slots, dr.p, n, di.p, dc.p);
+  c->launches += 1;
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  return GRB_OK;
+}
+
+int
+grb_hash_sequence(grb_ctx* c, const char* seq, size_t n, uint64_t* out)
+{
+  cudaSetDevice(c->device);
+  const unsigned h = c->h_seed.h, k = c->h_seed.k;
+  if (n < k + h - 1) {
+    return c->fail(GRB_ERR_ARG, "SeedNtHash: sequence length is smaller than k");
+  }
+  std::vector<uint64_t> words((n + 31) / 32 + 4, 0);
+  for (size_t i = 0; i < n; ++i) {
+    unsigned code;
+    switch (seq[i]) {
+      case 'A': case 'a': code = 0; break;
+      case 'C': case 'c': code = 1; break;
+      case 'G': case 'g': code = 2; break;
+      case 'T': case 't': code = 3; break;
+      default: return c->fail(GRB_ERR_ARG, "grb_hash_sequence: non-ACGT base");
+    }
+    words[i >> 5] |= (uint64_t)code << (2 * (i & 31));
+  }
+  const uint64_t frames = n - k + 1;
+  DevBuf<uint64_t> dw, dout;
+  cudaStream_t s = c->stream;
+  GRB_CUDA(c, dw.reserve(words.size(), 0, s));
+  GRB_CUDA(c, dout.reserve(frames * h, 0, s));
+  GRB_CUDA(c, cudaMemcpyAsync(dw.p, words.data(), words.size() * 8, cudaMemcpyHostToDevice, s));
+  k_hash_sequence<<<grid_for(frames, 128, c->sm_count * 16), 128, 0, s>>>(dw.p, (uint32_t)n,
+                                                                         c->d_seed, dout.p);
+  c->launches += 1;
+  GRB_CUDA(c, cudaMemcpyAsync(out, dout.p, frames * h * 8, cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  return GRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// selection loop
+// ------------------------------------------------------------------------------------------
+static int
+sel_prepare(grb_ctx* c, uint64_t max_len)
+{
+  cudaStream_t s = c->stream;
+  const uint64_t T = c->p.tile_length, h = c->h_seed.h, k = c->h_seed.k;
+  if (!c->sel_init) {
+    GrbSelParams& q = c->prm;
+    q.tile_len = (uint32_t)T;
+    q.k = (uint32_t)k;
+    q.h = (uint32_t)h;
+    q.cand_cap = (uint32_t)(T * h / 3 + 1);
+    q.table_size = (uint32_t)next_pow2(2 * T * h);
+    q.sw_words = (uint32_t)((T + k + 63) / 32 + 4);
+    q.silver = c->p.silver_path;
+    q.threshold = c->p.threshold;
+    q.unassigned_min = c->p.unassigned_min;
+    q.assigned_max = c->p.assigned_max;
+    q.block_size = c->p.block_size;
+    q.max_paths = c->p.max_paths;
+    q.target_bases = (uint64_t)(c->p.ratio * c->p.genome_size); // goldrush_path.cpp:1223
+    c->query_smem = sizeof(GrbSeedTables) + (size_t)q.sw_words * 8 + (size_t)q.table_size * 8;
+    if (c->query_smem > 200 * 1024) {
+      return c->fail(GRB_ERR_ARG, "tile_length * hash_num too large for the shared-memory vote "
+                                  "table (limit 12288)");
+    }
+    GRB_CUDA(c, cudaFuncSetAttribute(k_query<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)c->query_smem));
+    if (!c->d_state) {
+      GRB_CUDA(c, cudaMalloc(&c->d_state, sizeof(GrbSelState)));
+    }
+    GrbSelState st{};
+    st.curr_path = 1;
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_state, &st, sizeof st, cudaMemcpyHostToDevice, s));
+    GRB_CUDA(c, cudaStreamSynchronize(s));
+    GRB_CUDA(c, c->b_plan.reserve(1, 0, s));
+    c->sel_init = true;
+    c->sel_finished = false;
+  }
+  const uint64_t tiles = std::max<uint64_t>(1, max_len / T);
+  if (tiles > c->sc_tiles) {
+    const uint64_t cap = c->prm.cand_cap;
+    GRB_CUDA(c, c->b_stash.reserve(tiles * T * h, 0, s));
+    GRB_CUDA(c, c->b_best_id.reserve(tiles, 0, s));
+    GRB_CUDA(c, c->b_best_count.reserve(tiles, 0, s));
+    GRB_CUDA(c, c->b_n_cand.reserve(tiles, 0, s));
+    GRB_CUDA(c, c->b_cand_id.reserve(tiles * cap, 0, s));
+    GRB_CUDA(c, c->b_cand_cnt.reserve(tiles * cap, 0, s));
+    GRB_CUDA(c, c->b_tile_id.reserve(tiles, 0, s));
+    GRB_CUDA(c, c->b_tile_as.reserve(tiles, 0, s));
+    GRB_CUDA(c, c->b_snap.reserve(tiles + 2, 0, s));
+    c->sc_tiles = tiles;
+  }
+  const uint64_t round_tiles = std::min<uint64_t>(tiles, 64 * c->p.block_size);
+  const uint64_t tab = next_pow2(2 * round_tiles * T * h);
+  if (tab > c->sc_tab) {
+    c->b_tab_key.release();
+    c->b_tab_mask.release();
+    GRB_CUDA(c, c->b_tab_key.reserve(tab, 0, s));
+    GRB_CUDA(c, c->b_tab_mask.reserve(tab, 0, s));
+    GRB_CUDA(c, cudaMemsetAsync(c->b_tab_key.p, 0xFF, c->b_tab_key.cap * 8, s));
+    GRB_CUDA(c, cudaMemsetAsync(c->b_tab_mask.p, 0, c->b_tab_mask.cap * 8, s));
+    c->sc_tab = tab;
+  }
+  c->sc = GrbSelScratch{ c->b_stash.p,   c->b_best_id.p, c->b_best_count.p, c->b_n_cand.p,
+                         c->b_cand_id.p, c->b_cand_cnt.p, c->b_tile_id.p,   c->b_tile_as.p,
+                         c->b_snap.p,    c->b_plan.p,     c->b_tab_key.p,   c->b_tab_mask.p };
+  return GRB_OK;
+}
+
+static void
+launch_read(grb_ctx* c, uint64_t r, uint64_t dec_idx, grb_decision* d_dec)
+{
+  cudaStream_t s = c->stream;
+  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  const uint64_t tiles = c->h_len[r] / T;
+  const unsigned qgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, 1024));
+  k_query<512><<<qgrid, 512, c->query_smem, s>>>(c->reads_dev(), c->d_seed, c->filt, c->prm, c->sc,
+                                                 c->d_state, r);
+  k_decide<<<1, 32, 0, s>>>(c->reads_dev(), c->prm, c->sc, c->d_state, d_dec, r, dec_idx);
+  c->launches += 2;
+  const uint64_t blocks = (tiles + c->p.block_size - 1) / c->p.block_size;
+  const uint64_t rounds = std::max<uint64_t>(1, (blocks + 63) / 64);
+  const uint64_t round_tiles = std::min<uint64_t>(std::max<uint64_t>(tiles, 1), 64 * c->p.block_size);
+  const uint32_t tab = (uint32_t)next_pow2(2 * round_tiles * T * h);
+  const unsigned cgrid = grid_for(round_tiles * T * h, 256, c->sm_count * 4);
+  const unsigned agrid = grid_for(tab, 256, c->sm_count * 4);
+  for (uint64_t round = 0; round < rounds; ++round) {
+    k_insert_collect<<<cgrid, 256, 0, s>>>(c->reads_dev(), c->prm, c->sc, c->d_state, r,
+                                           (uint32_t)round, tab);
+    k_insert_apply<<<agrid, 256, 0, s>>>(c->filt, c->sc, c->d_state, r, (uint32_t)round, tab);
+    c->launches += 2;
+  }
+}
+
+int
+grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decisions,
+                 grb_path_stats* stats, uint32_t stats_cap, uint32_t* n_stats, int* finished)
+{
+  cudaSetDevice(c->device);
+  if (n_stats) {
+    *n_stats = 0;
+  }
+  if (!c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_select_reads before grb_finalize_bitvector");
+  }
+  if (first + count > c->n_reads) {
+    return c->fail(GRB_ERR_ARG, "grb_select_reads: range past the end of the read store");
+  }
+  cudaStream_t s = c->stream;
+  uint64_t max_len = 0;
+  for (uint64_t r = first; r < first + count; ++r) {
+    if (c->h_flags[r] & GRB_READ_PASS2) {
+      if (c->h_flags[r] & 4u) {
+        return c->fail(GRB_ERR_ARG, "a read with non-ACGT bases is flagged GRB_READ_PASS2");
+      }
+      max_len = std::max<uint64_t>(max_len, c->h_len[r]);
+    }
+  }
+  int rc = sel_prepare(c, max_len);
+  if (rc != GRB_OK) {
+    return rc;
+  }
+  GRB_CUDA(c, c->d_dec.reserve(std::max<uint64_t>(1, count), 0, s));
+  GRB_CUDA(c, cudaMemsetAsync(c->d_dec.p, 0, std::max<uint64_t>(1, count) * sizeof(grb_decision), s));
+  c->tic();
+  const uint64_t end = first + count;
+  uint64_t i = first;
+  uint64_t stop_at = c->sel_finished ? first : end; // reads at or past it were never reached
+  const uint64_t kChunk = 256;
+  while (i < end && !c->sel_finished) {
+    uint64_t launched = 0, j = i;
+    for (; j < end && launched < kChunk; ++j) {
+      if (c->h_flags[j] & GRB_READ_PASS2) {
+        launch_read(c, j, j - first, c->d_dec.p);
+        ++launched;
+      }
+    }
+    GrbSelState st;
+    GRB_CUDA(c, cudaMemcpyAsync(&st, c->d_state, sizeof st, cudaMemcpyDeviceToHost, s));
+    GRB_CUDA(c, cudaStreamSynchronize(s));
+    if (st.halt) {
+      if (st.n_snap && stats && n_stats && *n_stats < stats_cap) {
+        stats[(*n_stats)++] = st.snap;
+      }
+      if (st.finished) {
+        c->sel_finished = true;
+        stop_at = st.halt_read + 1;
+        break;
+      }
+      // rollover: reset_counts + reset_ID_vector, then resume after the read that triggered it
+      GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0,
+                                  std::max<uint64_t>(1, c->filt.pop) * sizeof(uint2), s));
+      st.halt = 0;
+      st.n_snap = 0;
+      GRB_CUDA(c, cudaMemcpyAsync(c->d_state, &st, sizeof st, cudaMemcpyHostToDevice, s));
+      GRB_CUDA(c, cudaStreamSynchronize(s));
+      i = st.halt_read + 1;
+      continue;
+    }
+    i = j;
+  }
+  GRB_CUDA(c, cudaMemcpyAsync(decisions, c->d_dec.p, count * sizeof(grb_decision),
+                              cudaMemcpyDeviceToHost, s));
+  c->toc();
+  GRB_CUDA(c, cudaGetLastError());
+  for (uint64_t r = first; r < end; ++r) {
+    grb_decision& d = decisions[r - first];
+    if (r >= stop_at) {
+      memset(&d, 0, sizeof d);
+    } else if (!(c->h_flags[r] & GRB_READ_PASS2)) {
+      memset(&d, 0, sizeof d);
+      d.verdict = GRB_SKIPPED;
+    }
+  }
+  if (finished) {
+    *finished = c->sel_finished ? 1 : 0;
+  }
+  return GRB_OK;
+}
+
+int
+grb_select_state(grb_ctx* c, grb_path_stats* current, uint64_t* curr_path, uint32_t* ids_inserted)
+{
+  cudaSetDevice(c->device);
+  if (!c->sel_init) {
+    return c->fail(GRB_ERR_STATE, "grb_select_state before grb_select_reads");
+  }
+  GrbSelState st;
+  GRB_CUDA(c, cudaMemcpyAsync(&st, c->d_state, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+  GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (current) {
+    *current = st.cur;
+  }
+  if (curr_path) {
+    *curr_path = st.curr_path;
+  }
+  if (ids_inserted) {
+    *ids_inserted = st.ids_inserted;
+  }
+  return GRB_OK;
+}
+
+int
+grb_query_read(grb_ctx* c, uint64_t read_idx, uint32_t* best_id, uint32_t* best_count,
+               uint32_t* n_cand, uint32_t* cand_ids, uint32_t* cand_counts, uint32_t cand_cap,
+               uint64_t* counters)
+{
+  cudaSetDevice(c->device);
+  if (!c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_query_read before grb_finalize_bitvector");
+  }
+  if (read_idx >= c->n_reads || (c->h_flags[read_idx] & 4u)) {
+    return c->fail(GRB_ERR_ARG, "grb_query_read: bad read index or read with non-ACGT bases");
+  }
+  int rc = sel_prepare(c, c->h_len[read_idx]);
+  if (rc != GRB_OK) {
+    return rc;
+  }
+  cudaStream_t s = c->stream;
+  const uint64_t tiles = c->h_len[read_idx] / c->p.tile_length;
+  DevBuf<GrbSelState> tmp; // throw-away state so the loop counters are untouched
+  GRB_CUDA(c, tmp.reserve(1, 0, s));
+  GRB_CUDA(c, cudaMemsetAsync(tmp.p, 0, sizeof(GrbSelState), s));
+  const unsigned qgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, 1024));
+  k_query<512><<<qgrid, 512, c->query_smem, s>>>(c->reads_dev(), c->d_seed, c->filt, c->prm, c->sc,
+                                                 tmp.p, read_idx);
+  c->launches += 1;
+  GrbSelState st;
+  GRB_CUDA(c, cudaMemcpyAsync(&st, tmp.p, sizeof st, cudaMemcpyDeviceToHost, s));
+  std::vector<uint32_t> ci(tiles * c->prm.cand_cap), cc(tiles * c->prm.cand_cap), nc(tiles);
+  if (tiles) {
+    GRB_CUDA(c, cudaMemcpyAsync(best_id, c->sc.best_id, tiles * 4, cudaMemcpyDeviceToHost, s));
+    GRB_CUDA(c, cudaMemcpyAsync(best_count, c->sc.best_count, tiles * 4, cudaMemcpyDeviceToHost, s));
+    GRB_CUDA(c, cudaMemcpyAsync(nc.data(), c->sc.n_cand, tiles * 4, cudaMemcpyDeviceToHost, s));
+    GRB_CUDA(c, cudaMemcpyAsync(ci.data(), c->sc.cand_id, ci.size() * 4, cudaMemcpyDeviceToHost, s));
+    GRB_CUDA(c, cudaMemcpyAsync(cc.data(), c->sc.cand_cnt, cc.size() * 4, cudaMemcpyDeviceToHost, s));
+  }
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  GRB_CUDA(c, cudaGetLastError());
+  for (uint64_t t = 0; t < tiles; ++t) {
+    // order candidates like the reference's sorted list: count descending, then id ascending
+    std::vector<std::pair<uint32_t, uint32_t>> v;
+    for (uint32_t j = 0; j < nc[t]; ++j) {
+      v.emplace_back(ci[t * c->prm.cand_cap + j], cc[t * c->prm.cand_cap + j]);
+    }
+    std::sort(v.begin(), v.end(), [](const auto& a, const auto& b) {
+      return a.second != b.second ? a.second > b.second : a.first < b.first;
+    });
+    n_cand[t] = nc[t];
+    for (uint32_t j = 0; j < v.size() && j < cand_cap; ++j) {
+      cand_ids[t * cand_cap + j] = v[j].first;
+      cand_counts[t * cand_cap + j] = v[j].second;
+    }
+  }
+  if (counters) {
+    counters[0] += st.cur.queries;
+    counters[1] += st.cur.hits;
+    counters[2] += st.cur.misses;
+  }
+  return GRB_OK;
+}
+
+int
+grb_insert_tiles(grb_ctx* c, uint64_t read_idx, uint32_t tile_start, uint32_t tile_end, uint32_t id)
+{
+  cudaSetDevice(c->device);
+  if (!c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_insert_tiles before grb_finalize_bitvector");
+  }
+  if (read_idx >= c->n_reads || (c->h_flags[read_idx] & 4u)) {
+    return c->fail(GRB_ERR_ARG, "grb_insert_tiles: bad read index or read with non-ACGT bases");
+  }
+  const uint64_t tiles = c->h_len[read_idx] / c->p.tile_length;
+  if (tile_start >= tile_end || tile_end > tiles) {
+    return c->fail(GRB_ERR_ARG, "grb_insert_tiles: empty or out-of-range tile range");
+  }
+  int rc = sel_prepare(c, c->h_len[read_idx]);
+  if (rc != GRB_OK) {
+    return rc;
+  }
+  cudaStream_t s = c->stream;
+  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  DevBuf<GrbSelState> tmp;
+  GRB_CUDA(c, tmp.reserve(1, 0, s));
+  GRB_CUDA(c, cudaMemsetAsync(tmp.p, 0, sizeof(GrbSelState), s));
+  const unsigned qgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, 1024));
+  k_query<512><<<qgrid, 512, c->query_smem, s>>>(c->reads_dev(), c->d_seed, c->filt, c->prm, c->sc,
+                                                 tmp.p, read_idx); // fills the rank stash
+  GrbReadPlan plan{};
+  plan.verdict = GRB_UNTRIMMED;
+  plan.trim_start = tile_start;
+  plan.trim_end = tile_end - 1;
+  plan.first_id = id;
+  plan.n_blocks = 1;
+  GRB_CUDA(c, cudaMemcpyAsync(c->sc.plan, &plan, sizeof plan, cudaMemcpyHostToDevice, s));
+  GrbSelParams q = c->prm;
+  q.block_size = tiles + 1; // the whole range is ONE insert call
+  const uint64_t n = (uint64_t)(tile_end - tile_start) * T * h;
+  const uint64_t tab = next_pow2(2 * n);
+  DevBuf<uint64_t> key, mask;
+  GRB_CUDA(c, key.reserve(tab, 0, s));
+  GRB_CUDA(c, mask.reserve(tab, 0, s));
+  GRB_CUDA(c, cudaMemsetAsync(key.p, 0xFF, tab * 8, s));
+  GRB_CUDA(c, cudaMemsetAsync(mask.p, 0, tab * 8, s));
+  GrbSelScratch sc = c->sc;
+  sc.tab_key = key.p;
+  sc.tab_mask = mask.p;
+  k_insert_collect<<<grid_for(n, 256, c->sm_count * 4), 256, 0, s>>>(c->reads_dev(), q, sc, tmp.p,
+                                                                    read_idx, 0, (uint32_t)tab);
+  k_insert_apply<<<grid_for(tab, 256, c->sm_count * 4), 256, 0, s>>>(c->filt, sc, tmp.p, read_idx, 0,
+                                                                    (uint32_t)tab);
+  c->launches += 3;
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  GRB_CUDA(c, cudaGetLastError());
+  return GRB_OK;
+}
+
+} // extern "C"

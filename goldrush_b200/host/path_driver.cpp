@@ -1,0 +1,520 @@
+// grb_run_path — the GoldRush-Path stage on top of the engine's C ABI: what the reference's main()
+// does between option parsing and exit (goldrush_path/goldrush_path.cpp:1096-1275), with the three
+// file passes of the reference collapsed into one ingest:
+//   ingest (K1) -> [ntcard (K5)] -> Phred median -> filters -> bit vector (K2+K4a) -> rank (K4b)
+//   -> ordered selection (K2+K3+K4c) -> silver-path FASTQ / golden-path FASTA writers.
+// Everything data-parallel runs on the device; this file only holds per-read bookkeeping
+// (O(#reads)), glibc-exact scalar maths, name handling and output.
+#include "goldrush_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <fcntl.h>
+#include <string>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+struct Log
+{
+  bool on;
+  void operator()(const char* fmt, ...) const
+  {
+    if (!on) {
+      return;
+    }
+    va_list ap;
+    va_start(ap, fmt);
+    vfprintf(stderr, fmt, ap);
+    va_end(ap);
+  }
+};
+
+struct Fnv
+{
+  uint64_t h = 1469598103934665603ull;
+  void add(const char* p, size_t n)
+  {
+    for (size_t i = 0; i < n; ++i) {
+      h ^= (unsigned char)p[i];
+      h *= 1099511628211ull;
+    }
+  }
+};
+
+struct OutFile
+{
+  FILE* f = nullptr;
+  bool write = false;
+  Fnv* digest = nullptr;
+  void open(const std::string& path)
+  {
+    close();
+    if (write) {
+      f = fopen(path.c_str(), "wb");
+    }
+  }
+  void put(const char* p, size_t n)
+  {
+    if (f) {
+      fwrite(p, 1, n, f);
+    }
+    digest->add(p, n);
+  }
+  void put(const std::string& s) { put(s.data(), s.size()); }
+  void close()
+  {
+    if (f) {
+      fclose(f);
+    }
+    f = nullptr;
+  }
+};
+
+double
+now_ms()
+{
+  return std::chrono::duration<double, std::milli>(
+           std::chrono::steady_clock::now().time_since_epoch())
+    .count();
+}
+
+int
+set_err(char* err, size_t cap, const std::string& msg, int code)
+{
+  if (err && cap) {
+    snprintf(err, cap, "%s", msg.c_str());
+  }
+  return code;
+}
+
+// calc_phred_average.cpp:45-58 over a byte range (host side: only for the few selected reads'
+// "Average Phred" log line)
+double
+sum_phred_host(const char* q, size_t n, const double* tab)
+{
+  double s = 0;
+  for (size_t i = 0; i < n; ++i) {
+    s += tab[(unsigned char)q[i]];
+  }
+  return s;
+}
+
+void
+log_path_stat(const Log& log, uint64_t curr_path, const grb_path_stats& s, double phred_sum)
+{
+  // goldrush_path.cpp:126-154
+  log("Visited %llu reads to generate %llu silver paths\n", (unsigned long long)s.valid_reads,
+      (unsigned long long)curr_path);
+  log("Saw: %llu tiles to generate %llu silver paths\n", (unsigned long long)s.total_tiles,
+      (unsigned long long)curr_path);
+  log("Assigned: %llu tiles to generate %llu silver paths\n", (unsigned long long)s.assigned_tiles,
+      (unsigned long long)curr_path);
+  log("Unassigned: %llu tiles to generate %llu silver paths\n",
+      (unsigned long long)s.unassigned_tiles, (unsigned long long)curr_path);
+  log("Total queries: %llu to generate %llu silver paths\n", (unsigned long long)s.queries,
+      (unsigned long long)curr_path);
+  log("Total hits: %llu to generate %llu silver paths\n", (unsigned long long)s.hits,
+      (unsigned long long)curr_path);
+  log("Total misses: %llu to generate %llu silver paths\n", (unsigned long long)s.misses,
+      (unsigned long long)curr_path);
+  log("Num reads: %llu in silver path %llu\n", (unsigned long long)s.num_reads_in_path,
+      (unsigned long long)curr_path);
+  const uint32_t avg = (uint32_t)(-10 * log10(phred_sum / s.inserted_bases));
+  log("Average Phred: %u in silver path %llu\n", avg, (unsigned long long)curr_path);
+}
+
+} // namespace
+
+extern "C" int
+grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_run_result* res,
+             char* err, size_t err_cap)
+{
+  const double t_wall0 = now_ms();
+  grb_run_result R{};
+  const Log log{ !o->quiet };
+  grb_params p = o->params;
+
+  // ---- input ----
+  const char* data = fastq;
+  size_t n = fastq_len;
+  void* map = nullptr;
+  size_t map_len = 0;
+  if (!data) {
+    const int fd = open(o->input_path ? o->input_path : "", O_RDONLY);
+    if (fd < 0) {
+      return set_err(err, err_cap, std::string("cannot open ") + (o->input_path ? o->input_path : ""),
+                     GRB_ERR_ARG);
+    }
+    struct stat sb;
+    fstat(fd, &sb);
+    map_len = (size_t)sb.st_size;
+    if (map_len) {
+      map = mmap(nullptr, map_len, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (map == MAP_FAILED) {
+        close(fd);
+        return set_err(err, err_cap, "mmap failed", GRB_ERR_NOMEM);
+      }
+      madvise(map, map_len, MADV_SEQUENTIAL);
+    }
+    close(fd);
+    data = (const char*)map;
+    n = map_len;
+  }
+  struct Unmap
+  {
+    void* m;
+    size_t l;
+    ~Unmap()
+    {
+      if (m) {
+        munmap(m, l);
+      }
+    }
+  } unmap{ map, map_len };
+
+  // ---- seeds (spaced_seeds.cpp) ----
+  const unsigned k = (unsigned)p.kmer_size, h = (unsigned)p.hash_num;
+  std::vector<std::string> seed_store(h, std::string(k + h + 2, '\0'));
+  std::vector<char*> seed_ptr(h);
+  for (unsigned i = 0; i < h; ++i) {
+    seed_ptr[i] = &seed_store[i][0];
+  }
+  const bool preset = o->seed_preset && o->seed_preset[0];
+  if (preset) {
+    log("Using preset spaced seed\nwith:\n\tspan: %zu\n\tweight: %ld\n", strlen(o->seed_preset),
+        (long)std::count(o->seed_preset, o->seed_preset + strlen(o->seed_preset), '1'));
+  } else {
+    log("Designing base symmetrical spaced seed\nUsing:\nspan: %u\nweight: %u\n", k,
+        (unsigned)p.weight);
+  }
+  if (grb_make_seed_pattern(o->seed_preset, k, (unsigned)p.weight, h, seed_ptr.data()) != GRB_OK) {
+    return set_err(err, err_cap, "cannot design a spaced seed for this k / w", GRB_ERR_ARG);
+  }
+  std::vector<const char*> seed_c(seed_ptr.begin(), seed_ptr.end());
+  p.seeds = seed_c.data();
+
+  grb_ctx* ctx = nullptr;
+  int rc = grb_create(&p, &ctx);
+  if (rc != GRB_OK) {
+    return set_err(err, err_cap, grb_last_error(nullptr), rc);
+  }
+  struct Guard
+  {
+    grb_ctx* c;
+    ~Guard() { grb_destroy(c); }
+  } guard{ ctx };
+  auto fail = [&](int code) { return set_err(err, err_cap, grb_last_error(ctx), code); };
+
+  // ---- K1: one pass over the file ----
+  if (n == 0 || data[0] != '@') {
+    log("Gold Path requires fastq format\n"); // goldrush_path.cpp:247-250
+    return set_err(err, err_cap, "Gold Path requires fastq format", GRB_ERR_FORMAT);
+  }
+  {
+    const size_t kChunk = (size_t)1 << 30;
+    size_t off = 0;
+    while (off < n) {
+      const size_t len = std::min(kChunk, n - off);
+      const int final = off + len == n;
+      size_t used = 0;
+      if ((rc = grb_reads_ingest_fastq(ctx, data + off, len, final, &used)) != GRB_OK) {
+        return fail(rc);
+      }
+      R.ms_ingest += grb_last_device_ms(ctx);
+      if (used == 0) {
+        if (final) {
+          break;
+        }
+        return set_err(err, err_cap, "FASTQ record larger than the 1 GiB ingest chunk", GRB_ERR_ARG);
+      }
+      off += used;
+    }
+  }
+  const uint64_t nreads = grb_reads_count(ctx);
+  std::vector<grb_read_meta> meta(nreads);
+  if (nreads && (rc = grb_reads_get_meta(ctx, 0, nreads, meta.data())) != GRB_OK) {
+    return fail(rc);
+  }
+  R.num_reads = nreads;
+
+  // ---- filter sizing (goldrush_path.cpp:1109-1123) ----
+  if (p.hash_universe == 0) {
+    if (o->ntcard) {
+      log("Calculating expected entries\n");
+      std::vector<uint64_t> per(h);
+      uint64_t total = 0;
+      if ((rc = grb_estimate_cardinality(ctx, n, per.data(), &total)) != GRB_OK) {
+        return fail(rc);
+      }
+      for (unsigned i = 0; i < h; ++i) {
+        log("Expected entries for seed pattern %s : %llu\n", seed_c[i], (unsigned long long)per[i]);
+      }
+      log("Total expected entries for seed patterns: %llu\n", (unsigned long long)total);
+      p.hash_universe = total;
+    } else {
+      p.hash_universe = grb_default_hash_universe(p.weight, p.genome_size, p.hash_num);
+    }
+  }
+
+  // ---- per-read Phred statistics from the device sums ----
+  std::vector<uint32_t> avg(nreads), delta(nreads);
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)nreads; ++i) {
+    grb_phred_finalize(meta[i].phred_first_half_sum, meta[i].phred_total_sum, meta[i].qual_len,
+                       &avg[i], &delta[i]);
+  }
+  // calc_min_phred_threshold (goldrush_path.cpp:79-107): median over the first 50000 reads that
+  // are long enough, in file order (the reference's sample is "first to arrive" among its threads)
+  if (p.phred_min == 0) {
+    log("Calculating minimum phred score via median\n");
+    const size_t cap = 50000;
+    std::vector<uint32_t> scores(cap, 0);
+    size_t cnt = 0;
+    for (uint64_t i = 0; i < nreads; ++i) {
+      if (meta[i].len < p.min_length) {
+        continue;
+      }
+      if (cnt >= cap) {
+        ++cnt;
+        break;
+      }
+      scores[cnt++] = avg[i];
+    }
+    std::sort(scores.begin(), scores.end(), std::greater<uint32_t>());
+    p.phred_min = std::max<uint32_t>(10u, scores[cnt / 2]);
+    if (o->verbose) {
+      log("Minimum phred score calculated with median: %u\n", p.phred_min);
+    }
+  }
+  R.phred_min = p.phred_min;
+
+  log("Calculating %s\nUsing:\n\ttile length: %llu\n\tblock size: %llu\n\tseed patterns: %llu\n"
+      "\tthreshold: %llu\n\tbase seed pattern: %s\n\tminimum unassigned tiles: %llu\n"
+      "\tmaximum assigned tiles: %llu\n\texpected hash space: %llu\n"
+      "\tminimum average phred quality score: %u\n"
+      "\tmaximum average phred delta between first and second half of read: %u\n"
+      "\toccupancy: %g\n\tjobs: %d\n",
+      p.silver_path ? (std::to_string(p.max_paths) + " silver path(s)").c_str() : "the golden path",
+      (unsigned long long)p.tile_length, (unsigned long long)p.block_size,
+      (unsigned long long)p.hash_num, (unsigned long long)p.threshold, seed_c[0],
+      (unsigned long long)p.unassigned_min, (unsigned long long)p.assigned_max,
+      (unsigned long long)p.hash_universe, p.phred_min, p.phred_delta, p.occupancy, o->jobs);
+
+  // ---- name filter (-f, goldrush_path.cpp:1163-1172) ----
+  std::unordered_set<std::string> filter_out;
+  if (o->filter_file && o->filter_file[0]) {
+    log("Using only reads not found in: %s\n", o->filter_file);
+    FILE* ff = fopen(o->filter_file, "r");
+    if (ff) {
+      char name[4096];
+      while (fscanf(ff, "%4095s", name) == 1) {
+        filter_out.insert(name);
+      }
+      fclose(ff);
+    }
+  }
+  auto read_id = [&](uint64_t i) {
+    const char* hdr = data + meta[i].hdr_off;
+    size_t l = 0;
+    while (l < meta[i].hdr_len && hdr[l] != ' ' && hdr[l] != '\t') {
+      ++l;
+    }
+    return std::string(hdr, l);
+  };
+
+  // ---- pass-1 filters (goldrush_path.cpp:261-301) ----
+  std::vector<uint8_t> flags(nreads, 0);
+  uint64_t by_len = 0, by_phred = 0, by_delta = 0, by_bases = 0, passed = 0;
+  for (uint64_t i = 0; i < nreads; ++i) {
+    if (meta[i].len < p.min_length) {
+      ++by_len;
+      continue;
+    }
+    if (avg[i] < p.phred_min || delta[i] >= p.phred_delta) {
+      by_phred += avg[i] < p.phred_min;
+      by_delta += delta[i] >= p.phred_delta;
+      filter_out.insert(read_id(i));
+      continue;
+    }
+    if (meta[i].non_acgt) {
+      ++by_bases;
+      filter_out.insert(read_id(i));
+      continue;
+    }
+    ++passed;
+    R.bases_pass1 += meta[i].len;
+    flags[i] = GRB_READ_PASS1;
+  }
+  // pass-2 eligibility (goldrush_path.cpp:907-932): long enough and name not filtered out
+  for (uint64_t i = 0; i < nreads; ++i) {
+    if (meta[i].len >= p.min_length && (filter_out.empty() || !filter_out.count(read_id(i)))) {
+      flags[i] |= GRB_READ_PASS2;
+    }
+  }
+  R.num_passed_reads = passed;
+
+  log("allocating bit vector\n");
+  const uint64_t filter_bits = grb_calc_optimal_size(p.hash_universe, 1, p.occupancy);
+  log("m_filterSize: %llu\n", (unsigned long long)filter_bits);
+  if ((rc = grb_filter_alloc(ctx, filter_bits)) != GRB_OK) {
+    return fail(rc);
+  }
+  R.filter_bits = filter_bits;
+  log("finished allocating bit vector\n");
+  log("opening: %s\n", o->input_path ? o->input_path : "(memory)");
+  log("inserting bit vector\n");
+  if (nreads && (rc = grb_reads_set_flags(ctx, 0, nreads, flags.data())) != GRB_OK) {
+    return fail(rc);
+  }
+  if ((rc = grb_build_bitvector(ctx)) != GRB_OK) {
+    log("%s\n", grb_last_error(ctx));
+    return fail(rc);
+  }
+  R.ms_pass1 = grb_last_device_ms(ctx);
+  if (o->verbose) {
+    log("num_passed_reads: %llu\nnum_reads: %llu\nnum_reads - num_passed_reads: %llu\n"
+        "num_reads - num_passed_reads / num_reads: %.0f\nnum_reads_skipped_by_phred: %llu\n"
+        "num_reads_skipped_by_delta: %llu\nnum_reads_skipped_by_length: %llu\n"
+        "num_reads_skipped_by_invalid_bases: %llu\nTotal reads skipped: %llu\n",
+        (unsigned long long)passed, (unsigned long long)nreads,
+        (unsigned long long)(nreads - passed), floor((double)(nreads - passed) / nreads),
+        (unsigned long long)by_phred, (unsigned long long)by_delta, (unsigned long long)by_len,
+        (unsigned long long)by_bases, (unsigned long long)(by_phred + by_delta + by_len + by_bases));
+  }
+  if (passed == 0) { // goldrush_path.cpp:327-334
+    log("Error: no reads passed the Phred score and min length requirements\n"
+        "Try again with a lower Phred threshold or lower min length\n");
+    return set_err(err, err_cap, "no reads passed the Phred score and min length requirements",
+                   GRB_ERR_ARG);
+  }
+  log("finished inserting bit vector\nin %.4f\n", R.ms_pass1 / 1e3);
+
+  uint64_t pop = 0;
+  if ((rc = grb_finalize_bitvector(ctx, &pop)) != GRB_OK) {
+    return fail(rc);
+  }
+  R.ms_rank = grb_last_device_ms(ctx);
+  R.pop = pop;
+
+  // ---- pass 2 ----
+  log("assigning tiles\n");
+  std::vector<grb_decision> dec(nreads);
+  std::vector<grb_path_stats> snaps(p.max_paths + 2);
+  uint32_t n_snaps = 0;
+  int finished = 0;
+  if (nreads && (rc = grb_select_reads(ctx, 0, nreads, dec.data(), snaps.data(),
+                                       (uint32_t)snaps.size(), &n_snaps, &finished)) != GRB_OK) {
+    return fail(rc);
+  }
+  R.ms_pass2 = grb_last_device_ms(ctx);
+  grb_path_stats cur{};
+  uint64_t curr_path = 1;
+  if ((rc = grb_select_state(ctx, &cur, &curr_path, nullptr)) != GRB_OK) {
+    return fail(rc);
+  }
+
+  // ---- outputs (goldrush_path.cpp:973-976,996-1002,1055-1070,1174-1179,182-184) ----
+  double tab[256];
+  for (int b = 0; b < 256; ++b) {
+    tab[b] = pow(10.0, -(int)((char)b - 33) / 10.0);
+  }
+  Fnv digest;
+  OutFile out;
+  out.write = o->write_outputs != 0;
+  out.digest = &digest;
+  const std::string prefix = o->prefix ? o->prefix : "goldrush_out";
+  out.open(p.silver_path ? prefix + "_1.fq" : prefix + ".fa");
+  const char first_char = p.silver_path ? '@' : '>';
+  uint32_t path_now = 1, snap_i = 0;
+  double phred_sum = 0;
+  uint64_t processed = 1; // the reference's `id` counter (goldrush_path.cpp:1225)
+  const uint64_t T = p.tile_length;
+  for (uint64_t i = 0; i < nreads; ++i) {
+    const grb_decision& d = dec[i];
+    if (d.verdict == GRB_NOT_VISITED) {
+      break;
+    }
+    if (d.verdict != GRB_SKIPPED) {
+      ++R.reads_visited;
+      R.bases_pass2 += (uint64_t)d.num_tiles * T;
+    }
+    if (d.verdict == GRB_UNTRIMMED || d.verdict == GRB_TRIMMED) {
+      if (d.path != path_now) { // a rollover happened right after the previous selected read
+        path_now = d.path;
+      }
+      const std::string id = read_id(i);
+      size_t s0 = 0, sl = meta[i].len;
+      if (d.verdict == GRB_TRIMMED) {
+        s0 = (size_t)d.trim_start * T;
+        sl = (d.trim_end == d.num_tiles - 1) ? meta[i].len - s0
+                                             : (size_t)(d.trim_end - d.trim_start + 1) * T;
+      }
+      std::string rec;
+      rec.reserve(2 * sl + id.size() + 32);
+      rec.push_back(first_char);
+      rec += id;
+      rec += d.verdict == GRB_TRIMMED ? "_trimmed\n" : "_untrimmed\n";
+      const size_t seq_at = rec.size();
+      rec.append(data + meta[i].seq_off + s0, sl);
+      for (size_t j = seq_at; j < rec.size(); ++j) { // SeqReader folds the sequence to upper case
+        rec[j] = (char)toupper((unsigned char)rec[j]);
+      }
+      rec.push_back('\n');
+      const size_t ql = std::min<size_t>(sl, meta[i].qual_len > s0 ? meta[i].qual_len - s0 : 0);
+      if (p.silver_path) {
+        rec += "+\n";
+        rec.append(data + meta[i].qual_off + s0, ql);
+        rec.push_back('\n');
+      }
+      out.put(rec);
+      ++R.reads_selected;
+      R.bases_selected += sl;
+      phred_sum += sum_phred_host(data + meta[i].qual_off + s0, ql, tab);
+      // silver_path_check (goldrush_path.cpp:156-187): a snapshot was taken right after this read
+      if (snap_i < n_snaps && snaps[snap_i].rollover_read == i) {
+        if (o->verbose) {
+          log_path_stat(log, path_now, snaps[snap_i], phred_sum);
+        }
+        ++snap_i;
+        phred_sum = 0;
+        if (path_now + 1 <= p.max_paths) {
+          out.open(prefix + "_" + std::to_string(path_now + 1) + ".fq");
+        }
+      }
+    }
+    ++processed;
+    if (processed % 10000 == 0) {
+      log("processed %llu reads\n", (unsigned long long)processed);
+    }
+  }
+  out.close();
+  R.paths = (uint32_t)curr_path;
+  if (!finished) {
+    if (p.silver_path && p.max_paths > curr_path) { // goldrush_path.cpp:1257-1264
+      log("WARNING: Expected %llu silver paths, but only %llu generated.\n"
+          "Possible reasons include:\n\t- Input reads sorted by chromosome/position\n"
+          "\t- Genome size set too large\n",
+          (unsigned long long)p.max_paths, (unsigned long long)curr_path);
+    }
+    if (o->verbose) {
+      log_path_stat(log, curr_path, cur, phred_sum);
+    }
+    log("assigned\nin %.4f\n", R.ms_pass2 / 1e3);
+  }
+  R.launches = grb_launch_count(ctx);
+  R.out_digest = digest.h;
+  R.ms_wall = now_ms() - t_wall0;
+  if (res) {
+    *res = R;
+  }
+  return GRB_OK;
+}

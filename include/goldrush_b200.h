@@ -94,7 +94,7 @@ typedef struct grb_read_meta
   double phred_first_half_sum; /* running sum captured at i == n/2 - 1 (calc_phred_average.cpp:26-28) */
   double phred_total_sum;
   uint32_t non_acgt; /* 1 if the sequence holds a byte outside ACGTacgt (goldrush_path.cpp:293) */
-  uint32_t pad;
+  uint32_t qual_len; /* bytes of the quality line (the n of calc_phred_average) */
 } grb_read_meta;
 
 /* Decodes every complete 4-line record in bytes[0, n) and appends it to the read store.
@@ -163,7 +163,8 @@ typedef struct grb_path_stats
   uint64_t misses;
   uint64_t num_reads_in_path;
   uint64_t inserted_bases;
-  double phred_sum_in_path;
+  uint64_t rollover_read; /* store index of the read whose insertion closed this path */
+  double phred_sum_in_path; /* filled by grb_run_path (host side); 0 from grb_select_reads */
 } grb_path_stats;
 
 /* Runs the selection loop over reads [first, first+count) of the store IN ORDER, continuing from
@@ -223,6 +224,8 @@ typedef struct grb_run_options
   int32_t verbose;         /* --verbose */
   int32_t debug;           /* --debug */
   int32_t write_outputs;   /* 0: decide only (bench) */
+  int32_t quiet;           /* 1: no stderr text at all */
+  int32_t jobs;            /* -j: host threads for the host-side bookkeeping (0 = default) */
 } grb_run_options;
 
 typedef struct grb_run_result
@@ -266,6 +269,16 @@ uint64_t grb_synth_num_reads(const grb_synth_params* p);
 char* grb_synth_fastq(const grb_synth_params* p, uint64_t first, uint64_t count,
                       uint64_t* out_len);
 void grb_free_host(void* p);
+
+/* ---- test hook: the device decision code (csrc/decide.cuh) compiled for the host, for CPU-side
+ * fuzzing against the oracle.  out_plan[9] = verdict, trim_start, trim_end, first_id, id_bump,
+ * n_blocks, n_assigned, out_bases lo/hi.  Never called by the product path. ---- */
+int grb_test_decide_host(uint32_t n_tiles, const uint32_t* best_id, const uint32_t* best_count,
+                         const uint32_t* n_cand, const uint32_t* cand_id, const uint32_t* cand_cnt,
+                         uint32_t cand_cap, uint64_t threshold, uint64_t read_len,
+                         uint64_t tile_length, uint64_t block_size, uint64_t unassigned_min,
+                         uint64_t assigned_max, uint32_t* ids_inserted, uint32_t* out_ids,
+                         uint8_t* out_assigned, uint32_t* out_plan);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,315 @@
+"""GPU parity tests: every kernel family of the engine against the CPU oracle on the same seeded
+inputs, through the C ABI, bit-exact (all of this path is integer / byte / index work; the two
+Phred sums are IEEE doubles added in the reference's order and must match to the last bit)."""
+import os
+
+import numpy as np
+import pytest
+
+import goldrush_b200 as grb
+import oracle_util as ou
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+
+SEED22 = "1011011110110111101101"
+GOLDEN = pu.load_golden()
+
+
+def _rand_seq(rng, n):
+    return bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)])
+
+
+def _fastq(records):
+    return b"".join(b"@" + n + b"\n" + s + b"\n+\n" + q + b"\n" for n, s, q in records)
+
+
+def _records(rng, n_reads, lo, hi, name=b"r"):
+    out = []
+    for i in range(n_reads):
+        L = int(rng.integers(lo, hi))
+        q = bytes((rng.integers(2, 41, size=L) + 33).astype(np.uint8))
+        out.append((name + str(i).encode() + b" c=" + str(i).encode(), _rand_seq(rng, L), q))
+    return out
+
+
+@pytest.mark.parametrize("k,w,h,preset", [(22, 16, 3, SEED22), (22, 16, 1, SEED22),
+                                          (20, 12, 2, ""), (24, 18, 4, ""), (32, 20, 5, "")])
+def test_hash_sequence_matches_oracle(k, w, h, preset):
+    seeds = grb.make_seed_pattern(preset, k, w, h)
+    rng = np.random.default_rng(k * 100 + h)
+    with grb.Engine(seeds, genome_size=1000000, weight=w) as e:
+        for n in [len(seeds[-1]), len(seeds[-1]) + 1, 64, 65, 1000, 1021, 4097]:
+            s = _rand_seq(rng, n)
+            got = e.hash_sequence(s)
+            exp = ou.hash_sequence(s, seeds)
+            assert got.shape == exp.shape
+            assert np.array_equal(got, exp), (n, k, h)
+        low = _rand_seq(rng, 500)
+        assert np.array_equal(e.hash_sequence(low.lower()), ou.hash_sequence(low, seeds))
+
+
+def test_phred_sums_bit_exact():
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, 3)
+    rng = np.random.default_rng(9)
+    with grb.Engine(seeds, genome_size=1000000, weight=16) as e:
+        for n in [1, 2, 3, 7, 100, 101, 25000]:
+            q = bytes((rng.integers(0, 60, size=n) + 33).astype(np.uint8))
+            first, total = e.phred_sums(q)
+            avg, delta, f0, t0 = ou.calc_phred_average(q)
+            assert (first, total) == (f0, t0), n
+            assert grb.phred_finalize(first, total, n) == (avg, delta)
+
+
+def test_ingest_decodes_ragged_fastq():
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, 3)
+    rng = np.random.default_rng(21)
+    recs = _records(rng, 300, 30, 3000)
+    # N, lower case, CRLF, a last record without newline
+    recs[3] = (recs[3][0], recs[3][1][:10] + b"N" + recs[3][1][11:], recs[3][2])
+    recs[5] = (recs[5][0], recs[5][1].lower(), recs[5][2])
+    recs[7] = (recs[7][0], recs[7][1][:5] + b"n" + recs[7][1][6:], recs[7][2])
+    data = _fastq(recs)
+    data = data.replace(b"@r9 c=9\n", b"@r9 c=9\r\n", 1)[:-1]
+    with grb.Engine(seeds, genome_size=1000000, weight=16) as e:
+        # feed in three chunks that split records at arbitrary bytes
+        cuts = [0, len(data) // 3 + 7, 2 * len(data) // 3 + 1, len(data)]
+        pos = 0
+        for i in range(3):
+            chunk = data[pos:cuts[i + 1]]
+            used = e.reads_ingest_fastq(chunk, final=(i == 2))
+            pos += used
+        assert pos == len(data)
+        assert e.reads_count() == len(recs)
+        meta = e.reads_get_meta()
+        for m, (name, seq, qual) in zip(meta, recs):
+            assert m.len == len(seq) and m.qual_len == len(qual)
+            assert data[m.seq_off:m.seq_off + m.len] == seq
+            assert data[m.qual_off:m.qual_off + m.qual_len] == qual
+            assert data[m.hdr_off:m.hdr_off + m.hdr_len] == name
+            assert m.non_acgt == (1 if (b"N" in seq or b"n" in seq) else 0)
+            avg, delta, f0, t0 = ou.calc_phred_average(qual)
+            assert (m.phred_first_half_sum, m.phred_total_sum) == (f0, t0)
+
+
+def _build_pair(rng, n_reads, lo, hi, seeds, bits, **params):
+    """Engine + oracle filter holding the same reads / bit vector."""
+    recs = _records(rng, n_reads, lo, hi)
+    e = grb.Engine(seeds, genome_size=1000000, weight=16, **params)
+    e.reads_ingest_fastq(_fastq(recs))
+    e.reads_set_flags(np.full(n_reads, 3, dtype=np.uint8))
+    e.filter_alloc(bits)
+    e.build_bitvector()
+    f = ou.Filter(bits, len(seeds))
+    for _, s, _ in recs:
+        f.insert_bv(ou.hash_sequence(s, seeds))
+    return e, f, recs
+
+
+@pytest.mark.parametrize("h,bits", [(3, 1000000 + 64), (1, 333376), (4, 5000000 + 128)])
+def test_bitvector_and_rank_match_oracle(h, bits):
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, h)
+    rng = np.random.default_rng(100 + h)
+    e, f, recs = _build_pair(rng, 40, 30, 6000, seeds, bits)
+    with e:
+        assert np.array_equal(e.copy_bitvector(), f.words())
+        pop = e.finalize_bitvector()
+        assert pop == f.setup()
+        pos = np.concatenate([rng.integers(0, bits, size=5000, dtype=np.uint64),
+                              np.array([0, 1, 63, 64, 191, 192, 193, bits - 1], dtype=np.uint64)])
+        r, b = e.rank(pos)
+        for p, rr, bb in zip(pos, r, b):
+            er, eb = f.rank(int(p))
+            assert (rr, bb) == (er, eb), p
+
+
+def _tile_hashes(seq, t, T, k, seeds):
+    tile = seq[t * T:t * T + T + k - 1]
+    return ou.hash_sequence(tile, seeds)
+
+
+@pytest.mark.parametrize("h,T,B", [(3, 1000, 10), (2, 200, 3), (4, 300, 1)])
+def test_query_vote_and_insert_match_oracle(h, T, B):
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, h)
+    k = 22
+    rng = np.random.default_rng(7 * h + T)
+    bits = 3000000 + 64
+    e, f, recs = _build_pair(rng, 12, 4 * T, 12 * T + 50, seeds, bits, tile_length=T, block_size=B)
+    with e:
+        pop = e.finalize_bitvector()
+        assert pop == f.setup()
+        next_id = 1
+        for step in range(3):
+            for ri, (_, seq, _) in enumerate(recs):
+                nt = len(seq) // T
+                bi, bc, nc, ci, cc, cnt = e.query_read(ri, nt, cand_cap=64)
+                exp_cnt = np.zeros(3, dtype=np.uint64)
+                for t in range(nt):
+                    hv = _tile_hashes(seq, t, T, k, seeds)
+                    obi, obc, on, oci, occ, oc = f.query_tile(hv, 64)
+                    exp_cnt += oc
+                    assert (bi[t], bc[t], nc[t]) == (obi, obc, on), (step, ri, t)
+                    assert list(ci[t][:on]) == list(oci) and list(cc[t][:on]) == list(occ)
+                assert np.array_equal(cnt, exp_cnt)
+                # insert a tile range as ONE call, ids chosen to exercise the reservoir rule
+                a = int(rng.integers(0, nt))
+                b = int(rng.integers(a + 1, nt + 1))
+                e.insert_tiles(ri, a, b, next_id)
+                flat = np.concatenate([_tile_hashes(seq, t, T, k, seeds).ravel() for t in range(a, b)])
+                f.insert_mibf(flat, next_id)
+                next_id += int(rng.integers(1, 3))
+            ranks = np.arange(pop, dtype=np.uint64)
+            ids, counts = e.get_ids(ranks)
+            for r in rng.integers(0, pop, size=20000):
+                assert (ids[r], counts[r]) == f.get(int(r)), (step, r)
+            nz = np.flatnonzero(counts)
+            for r in nz[:20000]:
+                assert (ids[r], counts[r]) == f.get(int(r))
+        # saturation bit is preserved by setData and masked by the query
+        some = np.flatnonzero(ids)[:50].astype(np.uint64)
+        e.set_ids(some, ids[some] | np.uint32(0x80000000), counts[some])
+        for r in some:
+            f.set(int(r), int(ids[r]) | 0x80000000, int(counts[r]))
+        seq = recs[0][1]
+        nt = len(seq) // T
+        bi, bc, nc, ci, cc, cnt = e.query_read(0, nt, cand_cap=64)
+        for t in range(nt):
+            obi, obc, on, oci, occ, oc = f.query_tile(_tile_hashes(seq, t, T, k, seeds), 64)
+            assert (bi[t], bc[t], nc[t]) == (obi, obc, on)
+        e.insert_tiles(0, 0, nt, 4242)
+        f.insert_mibf(np.concatenate([_tile_hashes(seq, t, T, k, seeds).ravel() for t in range(nt)]),
+                      4242)
+        ids2, counts2 = e.get_ids(some)
+        for r, i2, c2 in zip(some, ids2, counts2):
+            assert (i2, c2) == f.get(int(r))
+        e.reset_ids()
+        ids3, counts3 = e.get_ids(ranks)
+        assert not ids3.any() and not counts3.any()
+
+
+def _args_to_params(args):
+    """goldrush-path command line -> grb_run_path keyword arguments."""
+    m = {"-k": ("kmer_size", int), "-w": ("weight", int), "-h": ("hash_num", int),
+         "-t": ("tile_length", int), "-u": ("unassigned_min", int), "-a": ("assigned_max", int),
+         "-o": ("occupancy", float), "-x": ("threshold", int), "-b": ("block_size", int),
+         "-d": ("phred_delta", int), "-P": ("phred_min", int), "-r": ("ratio", float),
+         "-M": ("max_paths", int), "-m": ("min_length", int), "-H": ("hash_universe", int),
+         "-g": ("genome_size", lambda v: int(float(v)))}
+    kw, i = {}, 0
+    while i < len(args):
+        a = args[i]
+        if a == "-s":
+            kw["seed_preset"] = args[i + 1]
+            i += 2
+        elif a == "-f":
+            kw["filter_file"] = args[i + 1]
+            i += 2
+        elif a in m:
+            kw[m[a][0]] = m[a][1](args[i + 1])
+            i += 2
+        elif a == "--silver_path":
+            kw["silver_path"] = 1
+            i += 1
+        elif a == "--ntcard":
+            kw["ntcard"] = True
+            i += 1
+        elif a == "--verbose":
+            kw["verbose"] = True
+            i += 1
+        else:
+            raise ValueError(a)
+    return kw
+
+
+_product_outputs = {}
+
+
+def _product_outputs_for(case, workdir):
+    """Runs the engine through grb_run_path with the FASTQ in a HOST buffer."""
+    if case["name"] not in _product_outputs:
+        inp, extra = pu.make_input(case, workdir, _product_outputs_for)
+        with open(inp, "rb") as f:
+            data = f.read()
+        prefix = os.path.join(workdir, case["name"] + ".gpu")
+        for fn in os.listdir(workdir):
+            if fn.startswith(os.path.basename(prefix)):
+                os.remove(os.path.join(workdir, fn))
+        kw = _args_to_params(case["args"] + extra)
+        res = grb.run_path(data, input_path=inp, prefix=prefix, quiet=True, **kw)
+        outs = sorted((os.path.join(workdir, fn) for fn in os.listdir(workdir)
+                       if fn.startswith(os.path.basename(prefix))),
+                      key=lambda p: (len(p), p))
+        _product_outputs[case["name"]] = (outs, res, inp)
+    return _product_outputs[case["name"]][0]
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in pu.golden_cases.CASES])
+def test_selected_reads_match_reference_fixture(name, workdir):
+    """Silver / golden path files byte-identical to what the reference wrote for the same input."""
+    case = pu.case_by_name(name)
+    outs = _product_outputs_for(case, workdir)
+    g = GOLDEN[name]
+    assert pu.digest_outputs(outs) == g["outputs"]
+    res = _product_outputs[name][1]
+    stats = dict((k, v) for k, v in g["stats"] if k in ("m_filterSize:", "num_passed_reads:"))
+    assert res.filter_bits == stats["m_filterSize:"]
+    assert res.num_passed_reads == stats["num_passed_reads:"]
+
+
+@pytest.mark.parametrize("name", ["silver_default", "golden_lognormal_all_lengths", "ntcard_sizing",
+                                  "filter_list"])
+def test_cli_binary_matches_reference_fixture(name, workdir):
+    """The drop-in executable: same files AND the same --verbose counters on stderr."""
+    case = pu.case_by_name(name)
+    inp, extra = pu.make_input(case, workdir, _product_outputs_for)
+    rc, outs, err = pu.run_cli(pu.PRODUCT, case, inp, extra, workdir, "cli", jobs=4)
+    g = GOLDEN[name]
+    assert rc == g["exit_code"], err[-2000:]
+    assert pu.digest_outputs(outs) == g["outputs"]
+    assert pu.parse_stats(err) == g["stats"]
+
+
+def test_cli_error_paths(workdir):
+    import subprocess
+    fa = os.path.join(workdir, "x.fa")
+    with open(fa, "w") as f:
+        f.write(">a\nACGT\n")
+    base = [pu.PRODUCT, "-k", "22", "-w", "16", "-s", SEED22, "-g", "1000"]
+    p = subprocess.run(base + ["-i", fa], capture_output=True)
+    assert p.returncode == 1 and b"Gold Path requires fastq format" in p.stderr
+    p = subprocess.run([pu.PRODUCT, "-w", "16", "-g", "1000", "-i", fa], capture_output=True)
+    assert p.returncode == 1 and b"span of spaced seed cannot be 0" in p.stderr
+    p = subprocess.run(base[:-2] + ["-i", fa], capture_output=True)
+    assert p.returncode == 1 and b"genome size cannot be 0" in p.stderr
+    fq = os.path.join(workdir, "short.fq")
+    with open(fq, "w") as f:
+        f.write("@a\n" + "ACGT" * 100 + "\n+\n" + "I" * 400 + "\n")
+    p = subprocess.run(base + ["-i", fq, "-m", "20000"], capture_output=True)
+    assert p.returncode == 1 and b"no reads passed" in p.stderr
+
+
+def test_split_selection_calls_equal_one_call():
+    """grb_select_reads keeps its loop state between calls: two halves == one pass."""
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, 3)
+    sp = grb.api.synth_params(200000, 12.0, 5000, 31)
+    data = grb.synth_fastq(sp)
+    outs = []
+    for split in (False, True):
+        with grb.Engine(seeds, genome_size=200000, weight=16, tile_length=250, min_length=5000,
+                        silver_path=1, max_paths=3, ratio=0.9) as e:
+            e.reads_ingest_fastq(data)
+            n = e.reads_count()
+            e.reads_set_flags(np.full(n, 3, dtype=np.uint8))
+            e.filter_alloc(grb.calc_optimal_size(grb.default_hash_universe(16, 200000, 3), 1, 0.1))
+            e.build_bitvector()
+            e.finalize_bitvector()
+            if split:
+                d1, s1, f1 = e.select_reads(0, n // 2)
+                d2, s2, f2 = e.select_reads(n // 2, n - n // 2)
+                dec, st = d1 + d2, s1 + s2
+            else:
+                dec, st, fin = e.select_reads()
+            outs.append(([(d.verdict, d.path, d.trim_start, d.trim_end) for d in dec],
+                         [(s.valid_reads, s.queries, s.hits, s.misses, s.rollover_read) for s in st]))
+    assert outs[0] == outs[1]
+    assert any(v[0] in (2, 3) for v in outs[0][0])

@@ -1,0 +1,172 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares, the host-side scalar
+helpers agree with the oracle (and with KATs taken from the reference), the device decision code
+(compiled for the host through the grb_test_decide_host hook) agrees with the oracle's smoothing on
+random tile vectors, and the engine fails loudly without a CUDA device."""
+import ctypes as C
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+import goldrush_b200 as grb
+import oracle_util as ou
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "goldrush_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = set(re.findall(r"\b(grb_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 35
+    L = grb.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in goldrush_b200.h but not exported"
+    assert declared == set(L._grb_symbols), "ctypes mirror out of sync with the header"
+
+
+def test_seed_pattern_kats():
+    # strings printed by the reference's make_seed_pattern in this image (glibc rand)
+    assert grb.make_seed_pattern("", 22, 16, 3) == [
+        "1111011100110011101111", "11110111001010011101111", "111101110010010011101111"]
+    assert grb.make_seed_pattern("1011011110110111101101", 22, 16, 3) == [
+        "1011011110110111101101", "10110111101010111101101", "101101111010010111101101"]
+    for k, w, h in [(20, 12, 2), (24, 18, 4), (22, 16, 1), (32, 20, 5), (21, 10, 2)]:
+        assert grb.make_seed_pattern("", k, w, h) == ou.make_seed_pattern("", k, w, h)
+
+
+def test_filter_sizing_kats():
+    # m_filterSize printed by the reference: G=1e6 -> 28473728, cfg sizes of 8(d)
+    assert grb.default_hash_universe(16, 1000000, 3) == 3000000
+    assert grb.calc_optimal_size(3000000, 1, 0.1) == 28473728
+    assert grb.calc_optimal_size(grb.default_hash_universe(16, 5000000, 3), 1, 0.1) == 142368384
+    assert grb.calc_optimal_size(grb.default_hash_universe(16, 100000000, 3), 1, 0.1) == 2847366528
+    assert grb.calc_optimal_size(grb.default_hash_universe(16, 3000000000, 3), 1, 0.1) == 61146729472
+    L = ou.lib()
+    rng = random.Random(5)
+    for _ in range(200):
+        g = rng.randrange(1, 4 * 10 ** 9)
+        w = rng.choice([10, 12, 14, 16, 18])
+        h = rng.randrange(1, 6)
+        occ = rng.choice([0.05, 0.1, 0.15, 0.2, 0.5])
+        hu = grb.default_hash_universe(w, g, h)
+        assert hu == L.grbo_default_hash_universe(w, g, h)
+        assert grb.calc_optimal_size(hu, 1, occ) == L.grbo_calc_optimal_size(hu, 1, occ)
+
+
+def test_phred_finalize_matches_oracle():
+    rng = np.random.default_rng(3)
+    for n in [1, 2, 3, 10, 101, 5000]:
+        for _ in range(20):
+            q = bytes((rng.integers(2, 41, size=n) + 33).astype(np.uint8))
+            avg, delta, first, total = ou.calc_phred_average(q)
+            assert grb.phred_finalize(first, total, n) == (avg, delta)
+
+
+def _random_votes(rng, n, ids_pool):
+    best_id, best_count, cands = [], [], []
+    for _ in range(n):
+        k = rng.choice([0, 0, 1, 1, 2, 3])
+        chosen = rng.sample(ids_pool, min(k, len(ids_pool)))
+        cl = sorted(((i, rng.choice([3, 4, 8, 11, 12, 30, 200])) for i in chosen), key=lambda t: t[0])
+        if cl and rng.random() < 0.85:
+            top = max(c for _, c in cl)
+            bid = min(i for i, c in cl if c == top)
+            best_id.append(bid)
+            best_count.append(top)
+        else:
+            cl = []
+            best_id.append(rng.choice(ids_pool + [0, 0]))
+            best_count.append(rng.choice([0, 1, 2]) if best_id[-1] else 0)
+            if best_count[-1] == 0:
+                best_id[-1] = 0
+        cands.append(cl)
+    return best_id, best_count, cands
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_device_decision_code_matches_oracle(seed):
+    L = grb.lib()
+    rng = random.Random(seed)
+    for it in range(1500):
+        n = rng.choice([0, 1, 2, 3, 4, 5, 8, 14, 15, 16, 20, 25, 40, 90])
+        pool = rng.choice([[1, 2], [5, 6, 7], [1, 2, 3, 9, 10, 50], [0xFFFFFFFF, 1, 2],
+                           [3, 4, 5, 6, 7, 8, 9, 10, 11]])
+        thr = rng.choice([0, 2, 5, 10])
+        best_id, best_count, cands = _random_votes(rng, n, pool)
+        cap = 8
+        bi = np.array(best_id + [0], dtype=np.uint32)
+        bc = np.array(best_count + [0], dtype=np.uint32)
+        nc = np.array([len(c) for c in cands] + [0], dtype=np.uint32)
+        ci = np.zeros((n + 1) * cap, dtype=np.uint32)
+        cc = np.zeros((n + 1) * cap, dtype=np.uint32)
+        for t, cl in enumerate(cands):
+            order = list(cl)
+            rng.shuffle(order)  # the device list is unordered
+            for j, (a, b) in enumerate(order):
+                ci[t * cap + j], cc[t * cap + j] = a, b
+        T, B = 100, rng.choice([1, 2, 3, 10])
+        u, a = rng.choice([0, 2, 5]), rng.choice([0, 1, 3])
+        read_len = n * T + rng.randrange(0, T)
+        ids_ins = C.c_uint32(rng.randrange(0, 1000))
+        ids0 = ids_ins.value
+        out_ids = np.zeros(n + 1, dtype=np.uint32)
+        out_as = np.zeros(n + 1, dtype=np.uint8)
+        plan = np.zeros(9, dtype=np.uint32)
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        L.grb_test_decide_host(n, p(bi), p(bc), p(nc), p(ci), p(cc), cap, thr, read_len, T, B, u, a,
+                               C.byref(ids_ins), p(out_ids), p(out_as), p(plan))
+        # oracle: threshold + smoothing, then the same decision restated in Python from
+        # goldrush_path.cpp:960-1053
+        o_ids, o_as, o_na = ou.smooth_tiles(best_id, [0] * n, cands, thr)
+        assert list(out_ids[:n]) == list(o_ids), (seed, it)
+        assert list(out_as[:n]) == list(o_as), (seed, it)
+        assert plan[6] == o_na
+        n_un = n - o_na
+        exp_ids = ids0
+        if n_un >= u and o_na <= a:
+            verdict, ts, te = 2, 0, max(n - 1, 0)
+            exp_ids = (exp_ids + 1 + read_len // (T * B)) & 0xFFFFFFFF
+        elif o_na == n:
+            verdict, ts, te = 4, 0, 0
+        else:
+            ls, le = ou.find_longest_stretch(list(o_as))
+            good, ts, te = ou.eval_flanks(ls, le, list(o_ids))
+            if good:
+                verdict = 3
+                exp_ids = (exp_ids + 1 + (te - ts) // B) & 0xFFFFFFFF
+            else:
+                verdict, ts, te = 4, 0, 0
+        assert plan[0] == verdict, (seed, it)
+        assert ids_ins.value == exp_ids
+        if verdict in (2, 3):
+            assert (plan[1], plan[2]) == (ts, te), (seed, it)
+            assert plan[3] == (ids0 + 1) & 0xFFFFFFFF
+
+
+def test_engine_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    seeds = grb.make_seed_pattern("1011011110110111101101", 22, 16, 3)
+    with pytest.raises(grb.GrbError) as e:
+        grb.Engine(seeds, genome_size=1000000, weight=16)
+    assert e.value.code == -2
+    with pytest.raises(grb.GrbError):
+        grb.run_path(b"@r\nACGT\n+\nIIII\n", kmer_size=22, weight=16, genome_size=1000,
+                     seed_preset="1011011110110111101101")
+
+
+def test_synth_generator_is_deterministic_and_thread_independent():
+    sp = grb.api.synth_params(50000, 3.0, 2000, 77)
+    a = grb.synth_fastq(sp)
+    os.environ["OMP_NUM_THREADS"] = "1"
+    b = grb.synth_fastq(sp, 0, grb.synth_num_reads(sp))
+    assert a == b
+    n = grb.synth_num_reads(sp)
+    assert a.count(b"\n") == 4 * n
+    # generating a sub-range gives the same records
+    part = grb.synth_fastq(sp, 5, 3)
+    assert part in a
