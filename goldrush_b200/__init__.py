@@ -5,6 +5,7 @@ sm_100a + host C++) and the ``build/goldrush-path`` executable.  This package is
 mirror of ``include/goldrush_b200.h`` that tests and ``bench.py`` use; it contains no algorithm and
 no CPU fallback: if the library is missing or no CUDA device is usable, calls raise.
 """
+from . import api  # noqa: F401
 from .api import (  # noqa: F401
     Engine,
     GrbError,
@@ -20,5 +21,7 @@ from .api import (  # noqa: F401
     phred_finalize,
     run_path,
     synth_fastq,
+    synth_fastq_raw,
+    free_host,
     synth_num_reads,
 )

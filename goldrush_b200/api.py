@@ -87,8 +87,16 @@ class SynthParams(C.Structure):
     ]
 
 
+READ_META_DTYPE = np.dtype([("hdr_off", "<u8"), ("seq_off", "<u8"), ("qual_off", "<u8"),
+                            ("hdr_len", "<u4"), ("len", "<u4"), ("phred_first_half_sum", "<f8"),
+                            ("phred_total_sum", "<f8"), ("non_acgt", "<u4"), ("qual_len", "<u4")])
+DECISION_DTYPE = np.dtype([("verdict", "u1"), ("pad", "u1", (3,)), ("path", "<u4"),
+                           ("trim_start", "<u4"), ("trim_end", "<u4"), ("num_tiles", "<u4"),
+                           ("num_assigned", "<u4")])
+
 VERDICTS = {0: "not_visited", 1: "skipped", 2: "untrimmed", 3: "trimmed", 4: "assigned"}
 READ_PASS1, READ_PASS2 = 1, 2
+KERNEL_CLASSES = ["fill", "rank", "query", "decide", "insert"]
 
 _lib = None
 
@@ -114,7 +122,7 @@ def lib():
         "grb_destroy": (None, [vp]),
         "grb_last_error": (C.c_char_p, [vp]),
         "grb_launch_count": (u64, [vp]),
-        "grb_reads_ingest_fastq": (i32, [vp, C.c_char_p, sz, i32, P(sz)]),
+        "grb_reads_ingest_fastq": (i32, [vp, vp, sz, i32, P(sz)]),
         "grb_reads_count": (u64, [vp]),
         "grb_reads_get_meta": (i32, [vp, u64, u64, P(ReadMeta)]),
         "grb_reads_set_flags": (i32, [vp, u64, u64, vp]),
@@ -140,7 +148,10 @@ def lib():
         "grb_or_words": (i32, [vp, vp, vp, u64]),
         "grb_sync": (i32, [vp]),
         "grb_last_device_ms": (dbl, [vp]),
-        "grb_run_path": (i32, [P(RunOptions), C.c_char_p, sz, P(RunResult), C.c_char_p, sz]),
+        "grb_stream": (i32, [vp, P(vp)]),
+        "grb_profile_enable": (i32, [vp, i32]),
+        "grb_kernel_time": (i32, [vp, i32, P(dbl), P(u64)]),
+        "grb_run_path": (i32, [P(RunOptions), vp, sz, P(RunResult), C.c_char_p, sz]),
         "grb_synth_num_reads": (u64, [P(SynthParams)]),
         "grb_synth_fastq": (vp, [P(SynthParams), u64, u64, P(u64)]),
         "grb_free_host": (None, [vp]),
@@ -236,10 +247,21 @@ class Engine:
             raise GrbError(rc, self._L.grb_last_error(self._h).decode())
 
     # K1
-    def reads_ingest_fastq(self, data: bytes, final=True):
+    def reads_ingest_fastq(self, data, final=True, nbytes=None):
+        """data: bytes, or a raw host address (int) with nbytes."""
         used = C.c_size_t()
-        self._chk(self._L.grb_reads_ingest_fastq(self._h, data, len(data), int(final), C.byref(used)))
+        n = len(data) if nbytes is None else nbytes
+        self._chk(self._L.grb_reads_ingest_fastq(self._h, data, n, int(final), C.byref(used)))
         return used.value
+
+    def reads_meta_array(self):
+        """All read metadata as one numpy structured array (fields of grb_read_meta)."""
+        n = self.reads_count()
+        arr = np.zeros(max(1, n), dtype=READ_META_DTYPE)
+        if n:
+            self._chk(self._L.grb_reads_get_meta(self._h, 0, n,
+                                                 C.cast(_ptr(arr), C.POINTER(ReadMeta))))
+        return arr[:n]
 
     def reads_count(self):
         return self._L.grb_reads_count(self._h)
@@ -353,6 +375,19 @@ class Engine:
                                            C.byref(fin)))
         return list(dec)[:count], list(st)[:ns.value], bool(fin.value)
 
+    def select_reads_array(self, first=0, count=None, stats_cap=64):
+        """select_reads with the decisions as one numpy structured array."""
+        if count is None:
+            count = self.reads_count() - first
+        dec = np.zeros(max(1, count), dtype=DECISION_DTYPE)
+        st = (PathStats * stats_cap)()
+        ns = C.c_uint32()
+        fin = C.c_int()
+        self._chk(self._L.grb_select_reads(self._h, first, count,
+                                           C.cast(_ptr(dec), C.POINTER(Decision)), st, stats_cap,
+                                           C.byref(ns), C.byref(fin)))
+        return dec[:count], list(st)[:ns.value], bool(fin.value)
+
     def select_state(self):
         st = PathStats()
         cp = C.c_uint64()
@@ -379,11 +414,27 @@ class Engine:
     def launch_count(self):
         return self._L.grb_launch_count(self._h)
 
+    def stream(self):
+        p = C.c_void_p()
+        self._chk(self._L.grb_stream(self._h, C.byref(p)))
+        return p.value
 
-def run_path(fastq: bytes = None, input_path=None, prefix="goldrush_out", seed_preset="",
+    def profile_enable(self, on=True):
+        self._chk(self._L.grb_profile_enable(self._h, int(on)))
+
+    def kernel_time(self, kclass):
+        """(milliseconds, launches) of one grb_kernel_class since profile_enable()."""
+        ms, n = C.c_double(), C.c_uint64()
+        self._chk(self._L.grb_kernel_time(self._h, KERNEL_CLASSES.index(kclass), C.byref(ms),
+                                          C.byref(n)))
+        return ms.value, n.value
+
+
+def run_path(fastq=None, input_path=None, prefix="goldrush_out", seed_preset="",
              filter_file=None, ntcard=False, verbose=False, write_outputs=True, quiet=True,
-             device=0, **params):
-    """grb_run_path: the whole GoldRush-Path stage (goldrush_path.cpp main())."""
+             device=0, nbytes=None, **params):
+    """grb_run_path: the whole GoldRush-Path stage (goldrush_path.cpp main()).
+    fastq: bytes, or a raw host address (int) with nbytes; None = read input_path."""
     L = lib()
     o = RunOptions()
     o.params = default_params(**params)
@@ -398,8 +449,9 @@ def run_path(fastq: bytes = None, input_path=None, prefix="goldrush_out", seed_p
     o.quiet = int(quiet)
     res = RunResult()
     err = C.create_string_buffer(1024)
-    rc = L.grb_run_path(C.byref(o), fastq, len(fastq) if fastq is not None else 0, C.byref(res),
-                        err, len(err))
+    if nbytes is None:
+        nbytes = len(fastq) if fastq is not None else 0
+    rc = L.grb_run_path(C.byref(o), fastq, nbytes, C.byref(res), err, len(err))
     if rc:
         raise GrbError(rc, err.value.decode())
     return res
@@ -412,6 +464,22 @@ def synth_params(genome_len, coverage, read_len, seed, err=0.01, n50=20000, qmin
 
 def synth_num_reads(sp):
     return lib().grb_synth_num_reads(C.byref(sp))
+
+
+def synth_fastq_raw(sp, first=0, count=None):
+    """(host address, bytes) of a malloc'ed FASTQ buffer; release with free_host()."""
+    L = lib()
+    if count is None:
+        count = L.grb_synth_num_reads(C.byref(sp)) - first
+    n = C.c_uint64()
+    p = L.grb_synth_fastq(C.byref(sp), first, count, C.byref(n))
+    if not p:
+        raise MemoryError("grb_synth_fastq")
+    return p, n.value
+
+
+def free_host(p):
+    lib().grb_free_host(p)
 
 
 def synth_fastq(sp, first=0, count=None) -> bytes:

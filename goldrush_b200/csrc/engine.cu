@@ -77,6 +77,61 @@ struct grb_ctx
   DevBuf<grb_decision> d_dec;
   size_t query_smem = 0;
 
+  // ---- per-kernel-class device timing (grb_profile_enable / grb_kernel_time) ----
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_free;
+  struct ProfPending
+  {
+    int k;
+    cudaEvent_t a, b;
+  };
+  std::vector<ProfPending> prof_pending;
+  cudaEvent_t prof_open = nullptr;
+  double prof_ms[GRB_K_COUNT] = {};
+  uint64_t prof_n[GRB_K_COUNT] = {};
+  cudaEvent_t prof_event()
+  {
+    cudaEvent_t e = nullptr;
+    if (!prof_free.empty()) {
+      e = prof_free.back();
+      prof_free.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
+  void kbegin()
+  {
+    if (prof_on) {
+      prof_open = prof_event();
+      cudaEventRecord(prof_open, stream);
+    }
+  }
+  void kend(int k, uint64_t n_launches = 1)
+  {
+    launches += n_launches;
+    if (prof_on) {
+      cudaEvent_t b = prof_event();
+      cudaEventRecord(b, stream);
+      prof_pending.push_back(ProfPending{ k, prof_open, b });
+      prof_n[k] += n_launches;
+      prof_open = nullptr;
+    }
+  }
+  // call after the stream has been synchronised
+  void kflush()
+  {
+    for (const ProfPending& q : prof_pending) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, q.a, q.b) == cudaSuccess) {
+        prof_ms[q.k] += ms;
+      }
+      prof_free.push_back(q.a);
+      prof_free.push_back(q.b);
+    }
+    prof_pending.clear();
+  }
+
   int fail(int code, const std::string& msg)
   {
     err = msg;
@@ -300,6 +355,10 @@ grb_destroy(grb_ctx* c)
   if (c->ev1) {
     cudaEventDestroy(c->ev1);
   }
+  c->kflush();
+  for (cudaEvent_t e : c->prof_free) {
+    cudaEventDestroy(e);
+  }
   cudaStream_t s = c->stream;
   delete c;
   if (s) {
@@ -311,6 +370,42 @@ int
 grb_sync(grb_ctx* c)
 {
   GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->kflush();
+  return GRB_OK;
+}
+
+int
+grb_stream(grb_ctx* c, void** cuda_stream)
+{
+  *cuda_stream = (void*)c->stream;
+  return GRB_OK;
+}
+
+int
+grb_profile_enable(grb_ctx* c, int on)
+{
+  cudaSetDevice(c->device);
+  GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->kflush();
+  c->prof_on = on != 0;
+  for (int k = 0; k < GRB_K_COUNT; ++k) {
+    c->prof_ms[k] = 0;
+    c->prof_n[k] = 0;
+  }
+  return GRB_OK;
+}
+
+int
+grb_kernel_time(grb_ctx* c, int kclass, double* ms, uint64_t* n_launches)
+{
+  if (kclass < 0 || kclass >= GRB_K_COUNT) {
+    return c->fail(GRB_ERR_ARG, "grb_kernel_time: unknown kernel class");
+  }
+  cudaSetDevice(c->device);
+  GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->kflush();
+  *ms = c->prof_ms[kclass];
+  *n_launches = c->prof_n[kclass];
   return GRB_OK;
 }
 
@@ -624,9 +719,10 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
     GRB_CUDA(c, cudaMemcpyAsync(c->d_chunk_first.p, chunk_first.data(), c->n_reads * 8,
                                 cudaMemcpyHostToDevice, s));
     c->tic();
+    c->kbegin();
     k_fill_bits<<<grid_for(chunk_read.size(), 1, c->sm_count * 16), 256, 0, s>>>(
       c->reads_dev(), c->d_seed, c->filt, c->d_chunk_read.p, c->d_chunk_first.p, chunk_read.size());
-    c->launches += 1;
+    c->kend(GRB_K_FILL);
   }
   c->toc();
   GRB_CUDA(c, cudaGetLastError());
@@ -654,10 +750,11 @@ grb_finalize_bitvector(grb_ctx* c, uint64_t* pop)
   GRB_CUDA(c, partial.reserve(n_cta, 0, s));
   GRB_CUDA(c, partial_off.reserve(n_cta + 1, 0, s));
   c->tic();
+  c->kbegin();
   k_rank_partial<<<(unsigned)n_cta, 256, 0, s>>>(c->filt.blocks, c->filt.n_blocks, partial.p);
   k_scan_u32<<<1, 1024, 0, s>>>(partial.p, partial_off.p, n_cta);
   k_rank_write<<<(unsigned)n_cta, 256, 0, s>>>(c->filt.blocks, c->filt.n_blocks, partial_off.p);
-  c->launches += 3;
+  c->kend(GRB_K_RANK, 3);
   uint64_t total = 0;
   GRB_CUDA(c, cudaMemcpyAsync(&total, partial_off.p + n_cta, 8, cudaMemcpyDeviceToHost, s));
   c->toc();
@@ -946,10 +1043,13 @@ launch_read(grb_ctx* c, uint64_t r, uint64_t dec_idx, grb_decision* d_dec)
   const uint64_t T = c->p.tile_length, h = c->h_seed.h;
   const uint64_t tiles = c->h_len[r] / T;
   const unsigned qgrid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, 1024));
+  c->kbegin();
   k_query<512><<<qgrid, 512, c->query_smem, s>>>(c->reads_dev(), c->d_seed, c->filt, c->prm, c->sc,
                                                  c->d_state, r);
+  c->kend(GRB_K_QUERY);
+  c->kbegin();
   k_decide<<<1, 32, 0, s>>>(c->reads_dev(), c->prm, c->sc, c->d_state, d_dec, r, dec_idx);
-  c->launches += 2;
+  c->kend(GRB_K_DECIDE);
   const uint64_t blocks = (tiles + c->p.block_size - 1) / c->p.block_size;
   const uint64_t rounds = std::max<uint64_t>(1, (blocks + 63) / 64);
   const uint64_t round_tiles = std::min<uint64_t>(std::max<uint64_t>(tiles, 1), 64 * c->p.block_size);
@@ -957,10 +1057,11 @@ launch_read(grb_ctx* c, uint64_t r, uint64_t dec_idx, grb_decision* d_dec)
   const unsigned cgrid = grid_for(round_tiles * T * h, 256, c->sm_count * 4);
   const unsigned agrid = grid_for(tab, 256, c->sm_count * 4);
   for (uint64_t round = 0; round < rounds; ++round) {
+    c->kbegin();
     k_insert_collect<<<cgrid, 256, 0, s>>>(c->reads_dev(), c->prm, c->sc, c->d_state, r,
                                            (uint32_t)round, tab);
     k_insert_apply<<<agrid, 256, 0, s>>>(c->filt, c->sc, c->d_state, r, (uint32_t)round, tab);
-    c->launches += 2;
+    c->kend(GRB_K_INSERT, 2);
   }
 }
 
@@ -1010,6 +1111,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
     GrbSelState st;
     GRB_CUDA(c, cudaMemcpyAsync(&st, c->d_state, sizeof st, cudaMemcpyDeviceToHost, s));
     GRB_CUDA(c, cudaStreamSynchronize(s));
+    c->kflush();
     if (st.halt) {
       if (st.n_snap && stats && n_stats && *n_stats < stats_cap) {
         stats[(*n_stats)++] = st.snap;

@@ -208,6 +208,22 @@ int grb_or_words(grb_ctx* ctx, void* dst, const void* src, uint64_t n_words);
 int grb_sync(grb_ctx* ctx);
 /* device timing of the last grb_build_bitvector / grb_select_reads / ingest call, milliseconds */
 double grb_last_device_ms(const grb_ctx* ctx);
+/* the cudaStream_t every kernel of this context is launched on (for the caller's own CUDA events) */
+int grb_stream(grb_ctx* ctx, void** cuda_stream);
+/* per-kernel-class device time: with profiling on, a CUDA event pair brackets every launch group of
+ * the classes below on the context's stream; grb_kernel_time returns the sums since the last
+ * grb_profile_enable (which also resets them).  Used by bench.py for the roofline. */
+typedef enum grb_kernel_class
+{
+  GRB_K_FILL = 0,   /* K2+K4a  k_fill_bits */
+  GRB_K_RANK = 1,   /* K4b     k_rank_partial + k_scan_u32 + k_rank_write */
+  GRB_K_QUERY = 2,  /* K2+K3   k_query */
+  GRB_K_DECIDE = 3, /*         k_decide */
+  GRB_K_INSERT = 4, /* K4c     k_insert_collect + k_insert_apply */
+  GRB_K_COUNT = 5
+} grb_kernel_class;
+int grb_profile_enable(grb_ctx* ctx, int on);
+int grb_kernel_time(grb_ctx* ctx, int kclass, double* ms, uint64_t* n_launches);
 
 /* ---- whole stage: what goldrush_path.cpp main() does between option parsing and exit ----
  * (goldrush_path.cpp:1096-1275).  fastq = the whole input file in host memory.  Writes
