@@ -96,7 +96,7 @@ DECISION_DTYPE = np.dtype([("verdict", "u1"), ("pad", "u1", (3,)), ("path", "<u4
 
 VERDICTS = {0: "not_visited", 1: "skipped", 2: "untrimmed", 3: "trimmed", 4: "assigned"}
 READ_PASS1, READ_PASS2 = 1, 2
-KERNEL_CLASSES = ["fill", "rank", "query", "decide", "insert"]
+KERNEL_CLASSES = ["fill", "rank", "query", "decide", "insert", "check"]
 
 _lib = None
 

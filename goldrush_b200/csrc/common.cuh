@@ -16,10 +16,20 @@
 //   word 0      number of set bits in all earlier blocks (filled by grb_finalize_bitvector)
 //   words 1..3  192 filter bits, LSB first
 // so one probe (bit test + rank) touches exactly one sector.  The ID / count pair of the slot
-// with that rank (MIBloomFilter::m_data + MIBFConstructSupport::m_counts) is one 8-byte uint2
-// {id, count}: a query reads one more sector, an insert read-modify-writes one.
+// with that rank (MIBloomFilter::m_data + MIBFConstructSupport::m_counts) is one 16-byte GrbSlot
+// {id, count, id0, epoch}: a query reads one more sector, an insert read-modify-writes one.
+// id0 / epoch are the engine's undo fields: the ID the slot held when batch `epoch` started, saved
+// by the first insert of that batch that rewrites the slot (kernels_batch.cuh).
 // ---------------------------------------------------------------------------------------------
 #define GRB_BLK_BITS 192ull
+
+struct __align__(16) GrbSlot
+{
+  uint32_t id;    // MIBloomFilter::m_data[rank] (bit 31 = saturation mask, MIBloomFilter.hpp:38)
+  uint32_t count; // MIBFConstructSupport::m_counts[rank]
+  uint32_t id0;   // id at the start of the batch that last rewrote the slot
+  uint32_t epoch; // serial number of that batch (0 = never rewritten since the last ID reset)
+};
 
 struct GrbFilterDev
 {
@@ -27,7 +37,7 @@ struct GrbFilterDev
   uint64_t bits;    // m = filter size in bits
   uint64_t inv;     // floor(2^64 / m) for the exact fast modulo
   uint64_t n_blocks;
-  uint2* slots;     // {id, count} per set bit, indexed by rank
+  GrbSlot* slots;   // one per set bit, indexed by rank
   uint64_t pop;
 };
 

@@ -17,14 +17,32 @@
 #define GRB_HD inline
 #endif
 
+// The smoothing code reads the per-tile votes through three accessors, so the same source serves
+// the candidate-list layout below and the dense count matrix of the batch engine
+// (kernels_batch.cuh: GrbMatrixVotes):
+//   best_id(i), best_count(i)   arg-max id of tile i (ties -> smallest id) and its count
+//   cand_count(i, id)           count of `id` in tile i if it is > 2 (a "candidate"), else 0
 struct GrbTileVotes
 {
-  const uint32_t* best_id;    // [n] arg-max id (ties -> smallest id), 0 if the tile saw no id
-  const uint32_t* best_count; // [n]
-  const uint32_t* n_cand;     // [n] ids with count > 2
-  const uint32_t* cand_id;    // [n * cand_cap]
-  const uint32_t* cand_cnt;   // [n * cand_cap]
+  const uint32_t* best_id_;    // [n] arg-max id (ties -> smallest id), 0 if the tile saw no id
+  const uint32_t* best_count_; // [n]
+  const uint32_t* n_cand;      // [n] ids with count > 2
+  const uint32_t* cand_id;     // [n * cand_cap]
+  const uint32_t* cand_cnt;    // [n * cand_cap]
   uint32_t cand_cap;
+  GRB_HD uint32_t best_id(uint32_t i) const { return best_id_[i]; }
+  GRB_HD uint32_t best_count(uint32_t i) const { return best_count_[i]; }
+  GRB_HD uint32_t cand_count(uint32_t i, uint32_t id) const
+  {
+    const uint32_t n = n_cand[i];
+    const uint32_t* ids = cand_id + (uint64_t)i * cand_cap;
+    for (uint32_t j = 0; j < n; ++j) {
+      if (ids[j] == id) {
+        return cand_cnt[(uint64_t)i * cand_cap + j];
+      }
+    }
+    return 0;
+  }
 };
 
 GRB_HD bool
@@ -33,36 +51,24 @@ grb_near(uint32_t a, uint32_t b)
   return a == b || a == (uint32_t)(b + 1u) || a == (uint32_t)(b - 1u);
 }
 
-// count of `id` among tile i's candidates, 0 if absent
+// id[n], as[n] are outputs; snap[n + 2] is scratch.  Returns the number of assigned tiles.
+template<class Votes>
 GRB_HD uint32_t
-grb_cand_count(const GrbTileVotes& v, uint32_t i, uint32_t id)
-{
-  const uint32_t n = v.n_cand[i];
-  const uint32_t* ids = v.cand_id + (uint64_t)i * v.cand_cap;
-  for (uint32_t j = 0; j < n; ++j) {
-    if (ids[j] == id) {
-      return v.cand_cnt[(uint64_t)i * v.cand_cap + j];
-    }
-  }
-  return 0;
-}
-
-// id[n], as[n] are outputs; snap[n] is scratch.  Returns the number of assigned tiles.
-GRB_HD uint32_t
-grb_smooth_tiles(uint32_t n, const GrbTileVotes& v, uint64_t threshold, uint32_t* id, uint8_t* as,
+grb_smooth_tiles(uint32_t n, const Votes& v, uint64_t threshold, uint32_t* id, uint8_t* as,
                  uint32_t* snap)
 {
   for (uint32_t i = 0; i < n; ++i) {
-    id[i] = v.best_id[i];
+    id[i] = v.best_id(i);
     // the candidate list is sorted by count, so its head is the arg-max count whenever it is > 2
-    as[i] = (v.best_count[i] > 2 && v.best_count[i] > threshold) ? 1 : 0;
+    const uint32_t bc = v.best_count(i);
+    as[i] = (bc > 2 && bc > threshold) ? 1 : 0;
   }
   if (n >= 3) {
     // adopt the neighbour's id when it is one of this tile's candidates: forward, then backward
     for (uint32_t i = 1; i < n; ++i) {
       const uint32_t nb = id[i - 1];
-      if (id[i] != nb && v.n_cand[i]) {
-        const uint32_t c = grb_cand_count(v, i, nb);
+      if (id[i] != nb) {
+        const uint32_t c = v.cand_count(i, nb);
         if (c) {
           id[i] = nb;
           as[i] = c > threshold ? 1 : 0;
@@ -71,8 +77,8 @@ grb_smooth_tiles(uint32_t n, const GrbTileVotes& v, uint64_t threshold, uint32_t
     }
     for (uint32_t i = n - 1; i-- > 0;) {
       const uint32_t nb = id[i + 1];
-      if (id[i] != nb && v.n_cand[i]) {
-        const uint32_t c = grb_cand_count(v, i, nb);
+      if (id[i] != nb) {
+        const uint32_t c = v.cand_count(i, nb);
         if (c) {
           id[i] = nb;
           as[i] = c > threshold ? 1 : 0;

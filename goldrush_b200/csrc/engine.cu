@@ -5,10 +5,12 @@
 #include "kernels_filter.cuh"
 #include "kernels_ntcard.cuh"
 #include "kernels_select.cuh"
+#include "kernels_batch.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace {
 thread_local std::string g_create_error;
@@ -76,6 +78,19 @@ struct grb_ctx
   DevBuf<uint64_t> b_tab_key, b_tab_mask;
   DevBuf<grb_decision> d_dec;
   size_t query_smem = 0;
+  // batch engine (kernels_batch.cuh)
+  bool batch_mode = true;
+  uint32_t batch_reads = 128;  // reads per speculative batch
+  uint32_t batch_tiles = 8192; // tile budget per batch (a single longer read still forms a batch)
+  uint32_t dirty_bits_log2 = 28;
+  uint64_t bt_cap = 0;         // capacity of the per-batch buffers, in tiles
+  DevBuf<uint64_t> bb_stash;
+  DevBuf<uint32_t> bb_vt_n, bb_vt_id, bb_vt_cnt, bb_best_id, bb_best_count, bb_hits, bb_miss;
+  DevBuf<uint32_t> bb_dirty, bb_cmat;
+  DevBuf<uint64_t> bb_read_idx;      // chunk descriptors
+  DevBuf<uint32_t> bb_tile_first, bb_tile_read;
+  size_t check_smem = 0;
+  uint32_t fb_words = 0;
 
   // ---- per-kernel-class device timing (grb_profile_enable / grb_kernel_time) ----
   bool prof_on = false;
@@ -308,6 +323,17 @@ grb_create(const grb_params* p, grb_ctx** out)
     return bail(GRB_ERR_CUDA, std::string("CUDA init: ") + cudaGetErrorString(e));
   }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+  // GRB_ENGINE=serial keeps the one-read-at-a-time loop (kernels_select.cuh) for A/B checks;
+  // GRB_BATCH_READS overrides the speculative batch size
+  if (const char* e = getenv("GRB_ENGINE")) {
+    c->batch_mode = strcmp(e, "serial") != 0;
+  }
+  if (const char* e = getenv("GRB_BATCH_READS")) {
+    const long v = strtol(e, nullptr, 10);
+    if (v > 0 && v <= 65536) {
+      c->batch_reads = (uint32_t)v;
+    }
+  }
   if ((e = cudaMalloc(&c->d_seed, sizeof(GrbSeedTables))) != cudaSuccess ||
       (e = cudaMemcpy(c->d_seed, &c->h_seed, sizeof(GrbSeedTables), cudaMemcpyHostToDevice)) !=
         cudaSuccess) {
@@ -761,8 +787,8 @@ grb_finalize_bitvector(grb_ctx* c, uint64_t* pop)
   GRB_CUDA(c, cudaGetLastError());
   c->filt.pop = total;
   // m_data + m_counts (MIBloomFilter.hpp:165-184, MIBFConstructSupport.hpp:175-181), zeroed
-  GRB_CUDA(c, cudaMalloc(&c->filt.slots, std::max<uint64_t>(1, total) * sizeof(uint2)));
-  GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, std::max<uint64_t>(1, total) * sizeof(uint2), s));
+  GRB_CUDA(c, cudaMalloc(&c->filt.slots, (total + 1) * sizeof(GrbSlot)));
+  GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, (total + 1) * sizeof(GrbSlot), s));
   GRB_CUDA(c, cudaStreamSynchronize(s));
   c->finalized = true;
   if (pop) {
@@ -778,7 +804,7 @@ grb_reset_ids(grb_ctx* c)
   if (!c->finalized) {
     return c->fail(GRB_ERR_STATE, "grb_reset_ids before grb_finalize_bitvector");
   }
-  GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, std::max<uint64_t>(1, c->filt.pop) * sizeof(uint2),
+  GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, (c->filt.pop + 1) * sizeof(GrbSlot),
                               c->stream));
   return GRB_OK;
 }
@@ -1058,11 +1084,141 @@ launch_read(grb_ctx* c, uint64_t r, uint64_t dec_idx, grb_decision* d_dec)
   const unsigned agrid = grid_for(tab, 256, c->sm_count * 4);
   for (uint64_t round = 0; round < rounds; ++round) {
     c->kbegin();
-    k_insert_collect<<<cgrid, 256, 0, s>>>(c->reads_dev(), c->prm, c->sc, c->d_state, r,
-                                           (uint32_t)round, tab);
-    k_insert_apply<<<agrid, 256, 0, s>>>(c->filt, c->sc, c->d_state, r, (uint32_t)round, tab);
+    k_insert_collect<<<cgrid, 256, 0, s>>>(c->reads_dev(), c->prm, c->sc, c->sc.stash, c->d_state,
+                                           r, (uint32_t)round, tab);
+    k_insert_apply<<<agrid, 256, 0, s>>>(c->filt, c->sc, c->d_state, r, (uint32_t)round, tab,
+                                         nullptr, 0u);
     c->kend(GRB_K_INSERT, 2);
   }
+}
+
+// ---- batch engine -------------------------------------------------------------------------
+struct BatchPlan
+{
+  std::vector<uint64_t> read_idx;   // visited reads of the chunk, in order
+  std::vector<uint32_t> tile_first; // per batch: local prefix (nb + 1 entries each), concatenated
+  std::vector<uint32_t> tile_read;  // per batch: b of each tile, concatenated
+  struct Batch
+  {
+    uint32_t read0, nb, tf0, tr0, n_bt;
+  };
+  std::vector<Batch> batches;
+};
+
+static int
+batch_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles)
+{
+  cudaStream_t s = c->stream;
+  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  if (max_batch_tiles > c->bt_cap) {
+    const uint64_t n = max_batch_tiles;
+    const uint64_t cap = T * h;
+    c->bb_stash.release();
+    c->bb_vt_id.release();
+    c->bb_vt_cnt.release();
+    GRB_CUDA(c, c->bb_stash.reserve(n * T * h, 0, s));
+    GRB_CUDA(c, c->bb_vt_id.reserve(n * cap, 0, s));
+    GRB_CUDA(c, c->bb_vt_cnt.reserve(n * cap, 0, s));
+    GRB_CUDA(c, c->bb_vt_n.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_best_id.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_best_count.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_hits.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_miss.reserve(n, 0, s));
+    c->bt_cap = n;
+  }
+  GRB_CUDA(c, c->bb_dirty.reserve((1ull << c->dirty_bits_log2) / 32, 0, s));
+  if (max_read_tiles > 160) { // count matrix of a very long read spills to global memory
+    GRB_CUDA(c, c->bb_cmat.reserve(max_read_tiles * max_read_tiles, 0, s));
+  }
+  if (c->check_smem == 0) {
+    c->fb_words = (uint32_t)((T + 31) / 32 + 1);
+    c->check_smem = (size_t)c->fb_words * 4 + (size_t)c->prm.table_size * 8;
+    GRB_CUDA(c, cudaFuncSetAttribute(k_commit_check<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)c->check_smem));
+    GRB_CUDA(c, cudaFuncSetAttribute(k_spec_query<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)c->query_smem));
+    GRB_CUDA(c, cudaFuncSetAttribute(k_commit_decide<256>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  return GRB_OK;
+}
+
+static GrbBatchDev
+batch_dev(grb_ctx* c, const BatchPlan::Batch& b)
+{
+  GrbBatchDev d{};
+  d.read_idx = c->bb_read_idx.p + b.read0;
+  d.tile_first = c->bb_tile_first.p + b.tf0;
+  d.tile_read = c->bb_tile_read.p + b.tr0;
+  d.nb = b.nb;
+  d.n_bt = b.n_bt;
+  d.stash = c->bb_stash.p;
+  d.vt_n = c->bb_vt_n.p;
+  d.vt_id = c->bb_vt_id.p;
+  d.vt_cnt = c->bb_vt_cnt.p;
+  d.best_id = c->bb_best_id.p;
+  d.best_count = c->bb_best_count.p;
+  d.tile_hits = c->bb_hits.p;
+  d.tile_miss = c->bb_miss.p;
+  d.vt_cap = (uint32_t)(c->p.tile_length * c->h_seed.h);
+  d.dirty_mask = (uint32_t)((1ull << c->dirty_bits_log2) - 1);
+  d.dirty_bits = c->bb_dirty.p;
+  d.cmat = c->bb_cmat.p;
+  return d;
+}
+
+// speculative query of one batch, then the ordered commit of its reads
+static int
+launch_batch(grb_ctx* c, const BatchPlan& bp, const BatchPlan::Batch& b, uint64_t first,
+             grb_decision* d_dec)
+{
+  cudaStream_t s = c->stream;
+  const uint64_t T = c->p.tile_length, h = c->h_seed.h, B = c->p.block_size;
+  const GrbBatchDev bd = batch_dev(c, b);
+  GRB_CUDA(c, cudaMemsetAsync(c->bb_dirty.p, 0, (1ull << c->dirty_bits_log2) / 8, s));
+  k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
+  c->launches += 1;
+  c->kbegin();
+  k_spec_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
+    c->reads_dev(), c->d_seed, c->filt, c->prm, bd, c->d_state);
+  c->kend(GRB_K_QUERY);
+  for (uint32_t i = 0; i < b.nb; ++i) {
+    const uint64_t r = bp.read_idx[b.read0 + i];
+    const uint64_t tiles = c->h_len[r] / T;
+    const uint32_t bt0 = bp.tile_first[b.tf0 + i];
+    c->kbegin();
+    k_commit_check<256><<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, 4096)), 256,
+                          c->check_smem, s>>>(c->reads_dev(), c->filt, c->prm, bd, c->d_state, i,
+                                              c->fb_words);
+    c->kend(GRB_K_CHECK);
+    // shared memory of the decision kernel: 6 n + 2 + 2 us words, n bytes, n * nu words
+    const uint32_t n_cap = (uint32_t)std::max<uint64_t>(tiles, 1);
+    const uint32_t us = (uint32_t)next_pow2(2 * (uint64_t)n_cap);
+    const uint32_t cm_smem = tiles <= 160 ? 1u : 0u;
+    const size_t dsm = (size_t)(6 * n_cap + 2 + 2 * us) * 4 + ((n_cap + 15) / 16) * 16 +
+                       (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
+    c->kbegin();
+    k_commit_decide<256><<<1, 256, dsm, s>>>(c->reads_dev(), c->prm, bd, c->b_plan.p, c->d_state,
+                                             d_dec, i, r - first, n_cap, us, cm_smem);
+    c->kend(GRB_K_DECIDE);
+    const uint64_t blocks = (tiles + B - 1) / B;
+    const uint64_t rounds = std::max<uint64_t>(1, (blocks + 63) / 64);
+    const uint64_t round_tiles = std::min<uint64_t>(std::max<uint64_t>(tiles, 1), 64 * B);
+    const uint32_t tab = (uint32_t)next_pow2(2 * round_tiles * T * h);
+    const unsigned cgrid = grid_for(round_tiles * T * h, 256, c->sm_count * 4);
+    const unsigned agrid = grid_for(tab, 256, c->sm_count * 4);
+    for (uint64_t round = 0; round < rounds; ++round) {
+      c->kbegin();
+      k_insert_collect<<<cgrid, 256, 0, s>>>(c->reads_dev(), c->prm, c->sc,
+                                             bd.stash + (uint64_t)bt0 * T * h, c->d_state, r,
+                                             (uint32_t)round, tab);
+      k_insert_apply<<<agrid, 256, 0, s>>>(c->filt, c->sc, c->d_state, r, (uint32_t)round, tab,
+                                           bd.dirty_bits, bd.dirty_mask);
+      c->kend(GRB_K_INSERT, 2);
+    }
+  }
+  GRB_CUDA(c, cudaGetLastError());
+  return GRB_OK;
 }
 
 int
@@ -1099,13 +1255,65 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
   const uint64_t end = first + count;
   uint64_t i = first;
   uint64_t stop_at = c->sel_finished ? first : end; // reads at or past it were never reached
-  const uint64_t kChunk = 256;
+  const uint64_t kChunk = c->batch_mode ? 4ull * c->batch_reads : 256;
   while (i < end && !c->sel_finished) {
     uint64_t launched = 0, j = i;
-    for (; j < end && launched < kChunk; ++j) {
-      if (c->h_flags[j] & GRB_READ_PASS2) {
-        launch_read(c, j, j - first, c->d_dec.p);
+    if (c->batch_mode) {
+      // cut the next kChunk visited reads into batches and describe them to the device
+      BatchPlan bp;
+      const uint64_t T = c->p.tile_length;
+      uint64_t max_bt = 0;
+      for (; j < end && launched < kChunk; ++j) {
+        if (!(c->h_flags[j] & GRB_READ_PASS2)) {
+          continue;
+        }
+        const uint32_t tiles = (uint32_t)(c->h_len[j] / T);
+        if (bp.batches.empty() || bp.batches.back().nb >= c->batch_reads ||
+            (bp.batches.back().n_bt && bp.batches.back().n_bt + tiles > c->batch_tiles)) {
+          if (!bp.batches.empty()) {
+            bp.tile_first.push_back(bp.batches.back().n_bt);
+          }
+          bp.batches.push_back(BatchPlan::Batch{ (uint32_t)bp.read_idx.size(), 0,
+                                                 (uint32_t)bp.tile_first.size(),
+                                                 (uint32_t)bp.tile_read.size(), 0 });
+        }
+        BatchPlan::Batch& b = bp.batches.back();
+        bp.read_idx.push_back(j);
+        bp.tile_first.push_back(b.n_bt);
+        bp.tile_read.insert(bp.tile_read.end(), tiles, b.nb);
+        b.nb += 1;
+        b.n_bt += tiles;
+        max_bt = std::max<uint64_t>(max_bt, b.n_bt);
         ++launched;
+      }
+      if (!bp.batches.empty()) {
+        bp.tile_first.push_back(bp.batches.back().n_bt);
+        if ((rc = batch_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T)) != GRB_OK) {
+          return rc;
+        }
+        GRB_CUDA(c, c->bb_read_idx.reserve(bp.read_idx.size(), 0, s));
+        GRB_CUDA(c, c->bb_tile_first.reserve(bp.tile_first.size(), 0, s));
+        GRB_CUDA(c, c->bb_tile_read.reserve(std::max<size_t>(1, bp.tile_read.size()), 0, s));
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_read_idx.p, bp.read_idx.data(), bp.read_idx.size() * 8,
+                                    cudaMemcpyHostToDevice, s));
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_tile_first.p, bp.tile_first.data(),
+                                    bp.tile_first.size() * 4, cudaMemcpyHostToDevice, s));
+        if (!bp.tile_read.empty()) {
+          GRB_CUDA(c, cudaMemcpyAsync(c->bb_tile_read.p, bp.tile_read.data(),
+                                      bp.tile_read.size() * 4, cudaMemcpyHostToDevice, s));
+        }
+        for (const BatchPlan::Batch& b : bp.batches) {
+          if ((rc = launch_batch(c, bp, b, first, c->d_dec.p)) != GRB_OK) {
+            return rc;
+          }
+        }
+      }
+    } else {
+      for (; j < end && launched < kChunk; ++j) {
+        if (c->h_flags[j] & GRB_READ_PASS2) {
+          launch_read(c, j, j - first, c->d_dec.p);
+          ++launched;
+        }
       }
     }
     GrbSelState st;
@@ -1123,7 +1331,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       }
       // rollover: reset_counts + reset_ID_vector, then resume after the read that triggered it
       GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0,
-                                  std::max<uint64_t>(1, c->filt.pop) * sizeof(uint2), s));
+                                  (c->filt.pop + 1) * sizeof(GrbSlot), s));
       st.halt = 0;
       st.n_snap = 0;
       GRB_CUDA(c, cudaMemcpyAsync(c->d_state, &st, sizeof st, cudaMemcpyHostToDevice, s));
@@ -1279,10 +1487,10 @@ grb_insert_tiles(grb_ctx* c, uint64_t read_idx, uint32_t tile_start, uint32_t ti
   GrbSelScratch sc = c->sc;
   sc.tab_key = key.p;
   sc.tab_mask = mask.p;
-  k_insert_collect<<<grid_for(n, 256, c->sm_count * 4), 256, 0, s>>>(c->reads_dev(), q, sc, tmp.p,
-                                                                    read_idx, 0, (uint32_t)tab);
-  k_insert_apply<<<grid_for(tab, 256, c->sm_count * 4), 256, 0, s>>>(c->filt, sc, tmp.p, read_idx, 0,
-                                                                    (uint32_t)tab);
+  k_insert_collect<<<grid_for(n, 256, c->sm_count * 4), 256, 0, s>>>(
+    c->reads_dev(), q, sc, sc.stash, tmp.p, read_idx, 0, (uint32_t)tab);
+  k_insert_apply<<<grid_for(tab, 256, c->sm_count * 4), 256, 0, s>>>(
+    c->filt, sc, tmp.p, read_idx, 0, (uint32_t)tab, nullptr, 0u);
   c->launches += 3;
   GRB_CUDA(c, cudaStreamSynchronize(s));
   GRB_CUDA(c, cudaGetLastError());

@@ -189,24 +189,24 @@ k_rank_query(GrbFilterDev f, const uint64_t* __restrict__ pos, uint64_t n,
 }
 
 __global__ void
-k_get_slots(const uint2* __restrict__ slots, const uint64_t* __restrict__ rank, uint64_t n,
+k_get_slots(const GrbSlot* __restrict__ slots, const uint64_t* __restrict__ rank, uint64_t n,
             uint32_t* __restrict__ ids, uint32_t* __restrict__ counts)
 {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    const uint2 s = slots[rank[i]];
-    ids[i] = s.x;
-    counts[i] = s.y;
+    const GrbSlot s = slots[rank[i]];
+    ids[i] = s.id;
+    counts[i] = s.count;
   }
 }
 
 __global__ void
-k_set_slots(uint2* __restrict__ slots, const uint64_t* __restrict__ rank, uint64_t n,
+k_set_slots(GrbSlot* __restrict__ slots, const uint64_t* __restrict__ rank, uint64_t n,
             const uint32_t* __restrict__ ids, const uint32_t* __restrict__ counts)
 {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    slots[rank[i]] = make_uint2(ids[i], counts[i]);
+    slots[rank[i]] = GrbSlot{ ids[i], counts[i], ids[i], 0u };
   }
 }
 

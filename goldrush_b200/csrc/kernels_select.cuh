@@ -27,6 +27,8 @@ struct GrbSelParams
 
 struct GrbSelState
 {
+  uint32_t epoch;         // serial number of the current batch (kernels_batch.cuh), never 0
+  uint32_t batch_inserts; // reads of the current batch that inserted so far
   uint32_t ids_inserted;
   uint32_t halt;     // set at a path rollover: later kernels are no-ops until the host resumes
   uint32_t finished; // the reference would have called exit(0) (goldrush_path.cpp:174-176)
@@ -53,7 +55,7 @@ struct GrbSelScratch
   uint64_t* tab_mask;
 };
 
-__device__ __forceinline__ uint32_t
+__host__ __device__ __forceinline__ uint32_t
 grb_mix32(uint32_t x)
 {
   x ^= x >> 16;
@@ -149,7 +151,7 @@ k_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilterD
 #pragma unroll
       for (unsigned i = 0; i < GRB_MAX_PATTERNS; ++i) {
         if (i < h) {
-          uint32_t v = __ldcg(&filt.slots[rank[i]].x);
+          uint32_t v = __ldcg(&filt.slots[rank[i]].id);
           if (v > GRB_SAT_MASK) {
             v &= ~GRB_SAT_MASK;
           }
@@ -316,8 +318,8 @@ k_decide(GrbReadsDev reads, GrbSelParams prm, GrbSelScratch sc, GrbSelState* __r
 // keeping calls that share a rank apart.  `round` selects insert blocks [64*round, 64*round+64).
 __global__ void __launch_bounds__(256)
 k_insert_collect(GrbReadsDev reads, GrbSelParams prm, GrbSelScratch sc,
-                 const GrbSelState* __restrict__ state, uint64_t read_idx, uint32_t round,
-                 uint32_t tab_size)
+                 const uint64_t* __restrict__ stash, const GrbSelState* __restrict__ state,
+                 uint64_t read_idx, uint32_t round, uint32_t tab_size)
 {
   const GrbReadPlan plan = *sc.plan;
   if (plan.n_blocks <= 64 * round || (plan.verdict != GRB_UNTRIMMED && plan.verdict != GRB_TRIMMED)) {
@@ -347,7 +349,7 @@ k_insert_collect(GrbReadsDev reads, GrbSelParams prm, GrbSelScratch sc,
     if (tl < k + p || f >= tl - (k + p) + 1) {
       continue; // stale-tail repeat of the last valid position: same rank, already registered
     }
-    const uint64_t key = sc.stash[((uint64_t)t * T + f) * h + p];
+    const uint64_t key = stash[((uint64_t)t * T + f) * h + p] & ~(1ull << 63);
     const uint32_t j = (uint32_t)((t - plan.trim_start) / B) - 64u * round;
     uint64_t slot = grb_mix64(key) & mask;
     while (true) {
@@ -367,7 +369,8 @@ k_insert_collect(GrbReadsDev reads, GrbSelParams prm, GrbSelScratch sc,
 // (MIBFConstructSupport.hpp:271-282, MIBloomFilter.hpp:593-602), then clears the table entry.
 __global__ void __launch_bounds__(256)
 k_insert_apply(GrbFilterDev filt, GrbSelScratch sc, const GrbSelState* __restrict__ state,
-               uint64_t read_idx, uint32_t round, uint32_t tab_size)
+               uint64_t read_idx, uint32_t round, uint32_t tab_size, uint32_t* __restrict__ dirty_bits,
+               uint32_t dirty_mask)
 {
   const GrbReadPlan plan = *sc.plan;
   if (plan.n_blocks <= 64 * round || (plan.verdict != GRB_UNTRIMMED && plan.verdict != GRB_TRIMMED)) {
@@ -383,15 +386,27 @@ k_insert_apply(GrbFilterDev filt, GrbSelScratch sc, const GrbSelState* __restric
       continue;
     }
     uint64_t m = sc.tab_mask[i];
-    uint2 s = filt.slots[key];
+    GrbSlot s = filt.slots[key];
+    const uint32_t orig = s.id;
     while (m) {
       const uint32_t j = __ffsll((long long)m) - 1;
       m &= m - 1;
       const uint32_t id = plan.first_id + 64u * round + j + plan.id_bump;
-      const uint32_t count = ++s.y;
+      const uint32_t count = ++s.count;
       if ((uint32_t)(key ^ (uint64_t)id) % count == count - 1) {
-        s.x = s.x > GRB_SAT_MASK ? (id | GRB_SAT_MASK) : id;
+        s.id = s.id > GRB_SAT_MASK ? (id | GRB_SAT_MASK) : id;
       }
+    }
+    if (dirty_bits && s.id != orig) {
+      // batch engine: remember the ID the slot held when the batch started (unless an earlier
+      // read of this batch already rewrote it) and flag the slot for the later reads' re-validation
+      const uint32_t epoch = state->epoch;
+      if (s.epoch != epoch) {
+        s.id0 = orig;
+        s.epoch = epoch;
+      }
+      const uint32_t hb = (uint32_t)key & dirty_mask;
+      atomicOr(&dirty_bits[hb >> 5], 1u << (hb & 31));
     }
     filt.slots[key] = s;
     sc.tab_key[i] = GRB_EMPTY_KEY;

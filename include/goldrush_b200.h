@@ -217,10 +217,11 @@ typedef enum grb_kernel_class
 {
   GRB_K_FILL = 0,   /* K2+K4a  k_fill_bits */
   GRB_K_RANK = 1,   /* K4b     k_rank_partial + k_scan_u32 + k_rank_write */
-  GRB_K_QUERY = 2,  /* K2+K3   k_query */
-  GRB_K_DECIDE = 3, /*         k_decide */
+  GRB_K_QUERY = 2,  /* K2+K3   k_spec_query (batch engine) / k_query (serial engine) */
+  GRB_K_DECIDE = 3, /*         k_commit_decide / k_decide */
   GRB_K_INSERT = 4, /* K4c     k_insert_collect + k_insert_apply */
-  GRB_K_COUNT = 5
+  GRB_K_CHECK = 5,  /*         k_commit_check: ordered re-validation of the speculative votes */
+  GRB_K_COUNT = 6
 } grb_kernel_class;
 int grb_profile_enable(grb_ctx* ctx, int on);
 int grb_kernel_time(grb_ctx* ctx, int kclass, double* ms, uint64_t* n_launches);

@@ -313,3 +313,64 @@ def test_split_selection_calls_equal_one_call():
                          [(s.valid_reads, s.queries, s.hits, s.misses, s.rollover_read) for s in st]))
     assert outs[0] == outs[1]
     assert any(v[0] in (2, 3) for v in outs[0][0])
+
+
+def _select_all(data, env, **params):
+    """Decisions + rollover snapshots + final counters of one full selection under `env`."""
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, params.pop("hash_num", 3))
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        with grb.Engine(seeds, weight=16, **params) as e:
+            e.reads_ingest_fastq(data)
+            n = e.reads_count()
+            e.reads_set_flags(np.full(n, 3, dtype=np.uint8))
+            e.filter_alloc(grb.calc_optimal_size(
+                grb.default_hash_universe(16, params["genome_size"], len(seeds)), 1, 0.1))
+            e.build_bitvector()
+            pop = e.finalize_bitvector()
+            dec, st, fin = e.select_reads()
+            cur, path, ids = e.select_state()
+            ranks = np.arange(min(pop, 2000000), dtype=np.uint64)
+            slot_ids, slot_counts = e.get_ids(ranks)
+            return ([(d.verdict, d.path, d.trim_start, d.trim_end, d.num_tiles, d.num_assigned)
+                     for d in dec],
+                    [(s.valid_reads, s.total_tiles, s.assigned_tiles, s.queries, s.hits, s.misses,
+                      s.num_reads_in_path, s.inserted_bases, s.rollover_read) for s in st],
+                    (cur.valid_reads, cur.queries, cur.hits, cur.misses, path, ids, fin),
+                    slot_ids.tobytes(), slot_counts.tobytes())
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("shape", [
+    dict(genome=300000, cov=14.0, read_len=6000, seed=41, tile_length=300, block_size=4,
+         max_paths=3, ratio=0.9, threshold=10, hash_num=3),
+    dict(genome=150000, cov=25.0, read_len=0, seed=42, tile_length=200, block_size=1,
+         max_paths=2, ratio=0.8, threshold=5, hash_num=2),
+    dict(genome=200000, cov=20.0, read_len=9000, seed=43, tile_length=500, block_size=10,
+         max_paths=1, ratio=0.9, threshold=10, hash_num=3, silver=0),
+])
+def test_batch_engine_equals_serial_engine(shape):
+    """The speculative batch + ordered commit must reproduce the one-read-at-a-time loop exactly:
+    same decisions, same per-path counters (queries / hits / misses included), same final ID and
+    count slots, for every batch size (1 = no speculation at all)."""
+    sp = grb.api.synth_params(shape["genome"], shape["cov"], shape["read_len"], shape["seed"],
+                              n50=7000)
+    data = grb.synth_fastq(sp)
+    params = dict(genome_size=shape["genome"], tile_length=shape["tile_length"],
+                  block_size=shape["block_size"], min_length=3 * shape["tile_length"],
+                  silver_path=shape.get("silver", 1), max_paths=shape["max_paths"],
+                  ratio=shape["ratio"], threshold=shape["threshold"], hash_num=shape["hash_num"])
+    ref = _select_all(data, {"GRB_ENGINE": "serial"}, **dict(params))
+    assert any(d[0] in (2, 3) for d in ref[0]) and any(d[0] == 4 for d in ref[0])
+    for b in ("1", "3", "32", "128"):
+        got = _select_all(data, {"GRB_ENGINE": "batch", "GRB_BATCH_READS": b}, **dict(params))
+        assert got[0] == ref[0], b
+        assert got[1] == ref[1], b
+        assert got[2] == ref[2], b
+        assert got[3] == ref[3] and got[4] == ref[4], b
