@@ -308,6 +308,7 @@ def bench_ours(args, w):
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     launches = eng.launch_count() - launches0
     ktime = {k: eng.kernel_time(k) for k in grb.api.KERNEL_CLASSES}
+    commit_prof = eng.commit_profile()
     eng.profile_enable(False)
 
     visited = dec["verdict"] >= 2
@@ -396,6 +397,7 @@ def bench_ours(args, w):
                        "l2": "inputs larger than L2 (filter blocks + ID slots + packed reads)",
                        "synth_s": round(t_synth, 1)},
             "kernels_ms_per_step": {k: v[0] / args.steps for k, v in ktime.items()},
+            "commit_profile_last_step": commit_prof,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }

@@ -96,7 +96,7 @@ DECISION_DTYPE = np.dtype([("verdict", "u1"), ("pad", "u1", (3,)), ("path", "<u4
 
 VERDICTS = {0: "not_visited", 1: "skipped", 2: "untrimmed", 3: "trimmed", 4: "assigned"}
 READ_PASS1, READ_PASS2 = 1, 2
-KERNEL_CLASSES = ["fill", "rank", "query", "decide", "insert", "check"]
+KERNEL_CLASSES = ["fill", "rank", "query", "decide", "insert", "smooth", "dedupe", "commit"]
 
 _lib = None
 
@@ -151,6 +151,7 @@ def lib():
         "grb_stream": (i32, [vp, P(vp)]),
         "grb_profile_enable": (i32, [vp, i32]),
         "grb_kernel_time": (i32, [vp, i32, P(dbl), P(u64)]),
+        "grb_commit_profile": (i32, [vp, P(u64)]),
         "grb_run_path": (i32, [P(RunOptions), vp, sz, P(RunResult), C.c_char_p, sz]),
         "grb_synth_num_reads": (u64, [P(SynthParams)]),
         "grb_synth_fastq": (vp, [P(SynthParams), u64, u64, P(u64)]),
@@ -421,6 +422,13 @@ class Engine:
 
     def profile_enable(self, on=True):
         self._chk(self._L.grb_profile_enable(self._h, int(on)))
+
+    def commit_profile(self):
+        out = (C.c_uint64 * 10)()
+        self._chk(self._L.grb_commit_profile(self._h, out))
+        names = ["check_cyc", "barrier1_cyc", "resmooth_cyc", "decide_cyc", "insert_cyc",
+                 "barrier2_cyc", "reads", "resmoothed", "inserted", "checked"]
+        return dict(zip(names, [int(x) for x in out]))
 
     def kernel_time(self, kclass):
         """(milliseconds, launches) of one grb_kernel_class since profile_enable()."""

@@ -319,7 +319,7 @@ grb_eval_flanks(int64_t ls, int64_t le, const uint32_t* id, uint32_t n, uint32_t
 }
 
 // What process_read decides for one visited read (goldrush_path.cpp:960-1080).
-struct GrbReadPlan
+struct alignas(16) GrbReadPlan
 {
   uint8_t verdict;      // grb_verdict
   uint32_t trim_start;  // first inserted tile

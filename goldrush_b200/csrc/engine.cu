@@ -86,11 +86,20 @@ struct grb_ctx
   uint64_t bt_cap = 0;         // capacity of the per-batch buffers, in tiles
   DevBuf<uint64_t> bb_stash;
   DevBuf<uint32_t> bb_vt_n, bb_vt_id, bb_vt_cnt, bb_best_id, bb_best_count, bb_hits, bb_miss;
-  DevBuf<uint32_t> bb_dirty, bb_cmat;
-  DevBuf<uint64_t> bb_read_idx;      // chunk descriptors
+  DevBuf<uint32_t> bb_dirty, bb_cmat, bb_uq, bb_nu, bb_uchg, bb_cm, bb_sp_id, bb_sp_nas, bb_inchg;
+  DevBuf<uint8_t> bb_sp_as;
+  DevBuf<GrbReadPlan> bb_sp_plan;
+  DevBuf<uint32_t> bb_sp_adv, bb_rd_hits, bb_rd_miss, bb_rd_q;
+  DevBuf<uint64_t> bb_dd_key, bb_dd_mask;
+  DevBuf<uint64_t> bb_read_idx, bb_cm_off, bb_dd_off; // chunk descriptors
+  DevBuf<uint32_t> bb_dd_size;
   DevBuf<uint32_t> bb_tile_first, bb_tile_read;
   size_t check_smem = 0;
   uint32_t fb_words = 0;
+  size_t commit_smem_max = 0;
+  uint32_t commit_ctas = 0;
+  DevBuf<unsigned long long> bb_barrier;
+  DevBuf<uint64_t> bb_dec_idx;
 
   // ---- per-kernel-class device timing (grb_profile_enable / grb_kernel_time) ----
   bool prof_on = false;
@@ -1096,17 +1105,25 @@ launch_read(grb_ctx* c, uint64_t r, uint64_t dec_idx, grb_decision* d_dec)
 struct BatchPlan
 {
   std::vector<uint64_t> read_idx;   // visited reads of the chunk, in order
+  std::vector<uint64_t> dec_idx;    // their index in the decisions array
   std::vector<uint32_t> tile_first; // per batch: local prefix (nb + 1 entries each), concatenated
   std::vector<uint32_t> tile_read;  // per batch: b of each tile, concatenated
+  std::vector<uint64_t> cm_off;     // per read: offset of its count matrix within the batch
+  std::vector<uint64_t> dd_off;     // per read: offset / size of its de-duplication table
+  std::vector<uint32_t> dd_size;
   struct Batch
   {
     uint32_t read0, nb, tf0, tr0, n_bt;
+    uint32_t max_tiles; // longest read of the batch, in tiles
+    uint64_t cm_words;  // sum of tiles^2
+    uint64_t dd_entries;
   };
   std::vector<Batch> batches;
 };
 
 static int
-batch_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles)
+batch_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, uint64_t max_cm_words,
+              uint64_t max_dd_entries)
 {
   cudaStream_t s = c->stream;
   const uint64_t T = c->p.tile_length, h = c->h_seed.h;
@@ -1124,7 +1141,29 @@ batch_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles)
     GRB_CUDA(c, c->bb_best_count.reserve(n, 0, s));
     GRB_CUDA(c, c->bb_hits.reserve(n, 0, s));
     GRB_CUDA(c, c->bb_miss.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_uq.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_sp_id.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_sp_as.reserve(n, 0, s));
     c->bt_cap = n;
+  }
+  GRB_CUDA(c, c->bb_sp_nas.reserve(c->batch_reads, 0, s));
+  GRB_CUDA(c, c->bb_inchg.reserve(c->batch_reads, 0, s));
+  GRB_CUDA(c, c->bb_sp_plan.reserve(c->batch_reads, 0, s));
+  GRB_CUDA(c, c->bb_sp_adv.reserve(c->batch_reads, 0, s));
+  GRB_CUDA(c, c->bb_rd_hits.reserve(c->batch_reads, 0, s));
+  GRB_CUDA(c, c->bb_rd_miss.reserve(c->batch_reads, 0, s));
+  GRB_CUDA(c, c->bb_rd_q.reserve(c->batch_reads, 0, s));
+  if (max_dd_entries > c->bb_dd_key.cap) {
+    c->bb_dd_key.release();
+    c->bb_dd_mask.release();
+    GRB_CUDA(c, c->bb_dd_key.reserve(max_dd_entries, 0, s));
+    GRB_CUDA(c, c->bb_dd_mask.reserve(max_dd_entries, 0, s));
+  }
+  GRB_CUDA(c, c->bb_nu.reserve(c->batch_reads, 0, s));
+  GRB_CUDA(c, c->bb_uchg.reserve(c->batch_reads, 0, s));
+  GRB_CUDA(c, c->bb_cm.reserve(std::max<uint64_t>(1, max_cm_words), 0, s));
+  if (max_read_tiles > 2048) {
+    return c->fail(GRB_ERR_ARG, "a read spans more than 2048 tiles: raise the tile length");
   }
   GRB_CUDA(c, c->bb_dirty.reserve((1ull << c->dirty_bits_log2) / 32, 0, s));
   if (max_read_tiles > 160) { // count matrix of a very long read spills to global memory
@@ -1133,12 +1172,23 @@ batch_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles)
   if (c->check_smem == 0) {
     c->fb_words = (uint32_t)((T + 31) / 32 + 1);
     c->check_smem = (size_t)c->fb_words * 4 + (size_t)c->prm.table_size * 8;
-    GRB_CUDA(c, cudaFuncSetAttribute(k_commit_check<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)c->check_smem));
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+    c->commit_smem_max = (size_t)max_optin - 2048; // static shared memory of the kernel
+    GRB_CUDA(c, cudaFuncSetAttribute(k_commit_batch<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)c->commit_smem_max));
+    int per_sm = 0;
+    GRB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_commit_batch<1024>, 1024,
+                                                              c->commit_smem_max));
+    if (per_sm < 1) {
+      return c->fail(GRB_ERR_CUDA, "k_commit_batch cannot be resident on this device");
+    }
+    c->commit_ctas = (uint32_t)c->sm_count;
+    GRB_CUDA(c, c->bb_barrier.reserve(1, 0, s));
+    GRB_CUDA(c, cudaFuncSetAttribute(k_spec_cmat<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     200 * 1024));
     GRB_CUDA(c, cudaFuncSetAttribute(k_spec_query<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)c->query_smem));
-    GRB_CUDA(c, cudaFuncSetAttribute(k_commit_decide<256>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   return GRB_OK;
 }
@@ -1164,6 +1214,24 @@ batch_dev(grb_ctx* c, const BatchPlan::Batch& b)
   d.dirty_mask = (uint32_t)((1ull << c->dirty_bits_log2) - 1);
   d.dirty_bits = c->bb_dirty.p;
   d.cmat = c->bb_cmat.p;
+  d.uq = c->bb_uq.p;
+  d.nu = c->bb_nu.p;
+  d.u_changed = c->bb_uchg.p;
+  d.cm = c->bb_cm.p;
+  d.cm_off = c->bb_cm_off.p + b.read0;
+  d.sp_tile_id = c->bb_sp_id.p;
+  d.sp_tile_as = c->bb_sp_as.p;
+  d.sp_n_as = c->bb_sp_nas.p;
+  d.in_changed = c->bb_inchg.p;
+  d.sp_plan = c->bb_sp_plan.p;
+  d.sp_adv = c->bb_sp_adv.p;
+  d.rd_hits = c->bb_rd_hits.p;
+  d.rd_miss = c->bb_rd_miss.p;
+  d.rd_queries = c->bb_rd_q.p;
+  d.dd_key = c->bb_dd_key.p;
+  d.dd_mask = c->bb_dd_mask.p;
+  d.dd_off = c->bb_dd_off.p + b.read0;
+  d.dd_size = c->bb_dd_size.p + b.read0;
   return d;
 }
 
@@ -1173,7 +1241,6 @@ launch_batch(grb_ctx* c, const BatchPlan& bp, const BatchPlan::Batch& b, uint64_
              grb_decision* d_dec)
 {
   cudaStream_t s = c->stream;
-  const uint64_t T = c->p.tile_length, h = c->h_seed.h, B = c->p.block_size;
   const GrbBatchDev bd = batch_dev(c, b);
   GRB_CUDA(c, cudaMemsetAsync(c->bb_dirty.p, 0, (1ull << c->dirty_bits_log2) / 8, s));
   k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
@@ -1182,40 +1249,48 @@ launch_batch(grb_ctx* c, const BatchPlan& bp, const BatchPlan::Batch& b, uint64_
   k_spec_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
     c->reads_dev(), c->d_seed, c->filt, c->prm, bd, c->d_state);
   c->kend(GRB_K_QUERY);
-  for (uint32_t i = 0; i < b.nb; ++i) {
-    const uint64_t r = bp.read_idx[b.read0 + i];
-    const uint64_t tiles = c->h_len[r] / T;
-    const uint32_t bt0 = bp.tile_first[b.tf0 + i];
-    c->kbegin();
-    k_commit_check<256><<<(unsigned)std::max<uint64_t>(1, std::min<uint64_t>(tiles, 4096)), 256,
-                          c->check_smem, s>>>(c->reads_dev(), c->filt, c->prm, bd, c->d_state, i,
-                                              c->fb_words);
-    c->kend(GRB_K_CHECK);
-    // shared memory of the decision kernel: 6 n + 2 + 2 us words, n bytes, n * nu words
-    const uint32_t n_cap = (uint32_t)std::max<uint64_t>(tiles, 1);
+  c->kbegin();
+  {
+    const uint32_t n_cap = std::max<uint32_t>(b.max_tiles, 1);
     const uint32_t us = (uint32_t)next_pow2(2 * (uint64_t)n_cap);
-    const uint32_t cm_smem = tiles <= 160 ? 1u : 0u;
-    const size_t dsm = (size_t)(6 * n_cap + 2 + 2 * us) * 4 + ((n_cap + 15) / 16) * 16 +
-                       (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
+    k_spec_cmat<256><<<b.nb, 256, (size_t)(5 * n_cap + 2 + 2 * us) * 4 + n_cap, s>>>(
+      c->reads_dev(), c->prm, bd, c->d_state, n_cap, us);
+  }
+  c->kend(GRB_K_SMOOTH);
+  if (b.dd_entries) {
+    GRB_CUDA(c, cudaMemsetAsync(c->bb_dd_key.p, 0xFF, b.dd_entries * 8, s));
+    GRB_CUDA(c, cudaMemsetAsync(c->bb_dd_mask.p, 0, b.dd_entries * 8, s));
     c->kbegin();
-    k_commit_decide<256><<<1, 256, dsm, s>>>(c->reads_dev(), c->prm, bd, c->b_plan.p, c->d_state,
-                                             d_dec, i, r - first, n_cap, us, cm_smem);
-    c->kend(GRB_K_DECIDE);
-    const uint64_t blocks = (tiles + B - 1) / B;
-    const uint64_t rounds = std::max<uint64_t>(1, (blocks + 63) / 64);
-    const uint64_t round_tiles = std::min<uint64_t>(std::max<uint64_t>(tiles, 1), 64 * B);
-    const uint32_t tab = (uint32_t)next_pow2(2 * round_tiles * T * h);
-    const unsigned cgrid = grid_for(round_tiles * T * h, 256, c->sm_count * 4);
-    const unsigned agrid = grid_for(tab, 256, c->sm_count * 4);
-    for (uint64_t round = 0; round < rounds; ++round) {
-      c->kbegin();
-      k_insert_collect<<<cgrid, 256, 0, s>>>(c->reads_dev(), c->prm, c->sc,
-                                             bd.stash + (uint64_t)bt0 * T * h, c->d_state, r,
-                                             (uint32_t)round, tab);
-      k_insert_apply<<<agrid, 256, 0, s>>>(c->filt, c->sc, c->d_state, r, (uint32_t)round, tab,
-                                           bd.dirty_bits, bd.dirty_mask);
-      c->kend(GRB_K_INSERT, 2);
+    k_spec_dedupe<<<grid_for(b.n_bt, 1, 1u << 20), 256, 0, s>>>(c->reads_dev(), c->prm, bd,
+                                                               c->d_state);
+    c->kend(GRB_K_DEDUPE);
+  }
+  // ---- ordered commit: one persistent cooperative launch ----
+  {
+    const uint32_t n_cap = std::max<uint32_t>(b.max_tiles, 1);
+    const uint32_t us = (uint32_t)next_pow2(2 * (uint64_t)n_cap);
+    uint32_t cm_smem = n_cap <= 160 ? 1u : 0u;
+    size_t smem = ((size_t)c->fb_words + 2 * (size_t)c->prm.table_size + 3 * (size_t)us +
+                   6 * (size_t)n_cap + 2) * 4 + ((n_cap + 15) / 16) * 16 +
+                  (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
+    if (smem > c->commit_smem_max) {
+      return c->fail(GRB_ERR_ARG, "a read spans too many tiles for the commit kernel's shared "
+                                  "memory: raise the tile length");
     }
+    GRB_CUDA(c, cudaMemsetAsync(c->bb_barrier.p, 0, 8, s));
+    GrbReadsDev reads = c->reads_dev();
+    GrbBatchDev bdv = bd;
+    GrbSelState* st = c->d_state;
+    grb_decision* dec = d_dec;
+    const uint64_t* dec_idx = c->bb_dec_idx.p + b.read0;
+    unsigned long long* ctr = c->bb_barrier.p;
+    uint32_t fbw = c->fb_words, us_a = us, n_cap_a = n_cap;
+    void* args[] = { &reads, &c->filt, &c->prm, &bdv, &c->sc, &st, &dec, &dec_idx, &ctr,
+                     &fbw,   &us_a,    &n_cap_a, &cm_smem };
+    c->kbegin();
+    GRB_CUDA(c, cudaLaunchCooperativeKernel((void*)k_commit_batch<1024>, dim3(c->commit_ctas),
+                                            dim3(1024), args, smem, s));
+    c->kend(GRB_K_COMMIT);
   }
   GRB_CUDA(c, cudaGetLastError());
   return GRB_OK;
@@ -1262,7 +1337,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       // cut the next kChunk visited reads into batches and describe them to the device
       BatchPlan bp;
       const uint64_t T = c->p.tile_length;
-      uint64_t max_bt = 0;
+      uint64_t max_bt = 0, max_cm = 0, max_dd = 0;
       for (; j < end && launched < kChunk; ++j) {
         if (!(c->h_flags[j] & GRB_READ_PASS2)) {
           continue;
@@ -1275,10 +1350,20 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
           }
           bp.batches.push_back(BatchPlan::Batch{ (uint32_t)bp.read_idx.size(), 0,
                                                  (uint32_t)bp.tile_first.size(),
-                                                 (uint32_t)bp.tile_read.size(), 0 });
+                                                 (uint32_t)bp.tile_read.size(), 0, 0, 0, 0 });
         }
         BatchPlan::Batch& b = bp.batches.back();
         bp.read_idx.push_back(j);
+        bp.dec_idx.push_back(j - first);
+        bp.cm_off.push_back(b.cm_words);
+        bp.dd_off.push_back(b.dd_entries);
+        const uint64_t dd = (tiles >= 1 && tiles <= 64) ? next_pow2(2ull * tiles * T * c->h_seed.h) : 0;
+        bp.dd_size.push_back((uint32_t)dd);
+        b.dd_entries += dd;
+        max_dd = std::max(max_dd, b.dd_entries);
+        b.cm_words += (uint64_t)tiles * tiles;
+        b.max_tiles = std::max(b.max_tiles, tiles);
+        max_cm = std::max(max_cm, b.cm_words);
         bp.tile_first.push_back(b.n_bt);
         bp.tile_read.insert(bp.tile_read.end(), tiles, b.nb);
         b.nb += 1;
@@ -1288,13 +1373,25 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       }
       if (!bp.batches.empty()) {
         bp.tile_first.push_back(bp.batches.back().n_bt);
-        if ((rc = batch_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T)) != GRB_OK) {
+        if ((rc = batch_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_dd)) != GRB_OK) {
           return rc;
         }
         GRB_CUDA(c, c->bb_read_idx.reserve(bp.read_idx.size(), 0, s));
         GRB_CUDA(c, c->bb_tile_first.reserve(bp.tile_first.size(), 0, s));
         GRB_CUDA(c, c->bb_tile_read.reserve(std::max<size_t>(1, bp.tile_read.size()), 0, s));
         GRB_CUDA(c, cudaMemcpyAsync(c->bb_read_idx.p, bp.read_idx.data(), bp.read_idx.size() * 8,
+                                    cudaMemcpyHostToDevice, s));
+        GRB_CUDA(c, c->bb_dec_idx.reserve(bp.dec_idx.size(), 0, s));
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_dec_idx.p, bp.dec_idx.data(), bp.dec_idx.size() * 8,
+                                    cudaMemcpyHostToDevice, s));
+        GRB_CUDA(c, c->bb_dd_off.reserve(bp.dd_off.size(), 0, s));
+        GRB_CUDA(c, c->bb_dd_size.reserve(bp.dd_size.size(), 0, s));
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_dd_off.p, bp.dd_off.data(), bp.dd_off.size() * 8,
+                                    cudaMemcpyHostToDevice, s));
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_dd_size.p, bp.dd_size.data(), bp.dd_size.size() * 4,
+                                    cudaMemcpyHostToDevice, s));
+        GRB_CUDA(c, c->bb_cm_off.reserve(bp.cm_off.size(), 0, s));
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_cm_off.p, bp.cm_off.data(), bp.cm_off.size() * 8,
                                     cudaMemcpyHostToDevice, s));
         GRB_CUDA(c, cudaMemcpyAsync(c->bb_tile_first.p, bp.tile_first.data(),
                                     bp.tile_first.size() * 4, cudaMemcpyHostToDevice, s));
@@ -1378,6 +1475,22 @@ grb_select_state(grb_ctx* c, grb_path_stats* current, uint64_t* curr_path, uint3
   }
   if (ids_inserted) {
     *ids_inserted = st.ids_inserted;
+  }
+  return GRB_OK;
+}
+
+int
+grb_commit_profile(grb_ctx* c, uint64_t* out10)
+{
+  cudaSetDevice(c->device);
+  if (!c->sel_init) {
+    return c->fail(GRB_ERR_STATE, "grb_commit_profile before grb_select_reads");
+  }
+  GrbSelState st;
+  GRB_CUDA(c, cudaMemcpyAsync(&st, c->d_state, sizeof st, cudaMemcpyDeviceToHost, c->stream));
+  GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < 10; ++i) {
+    out10[i] = st.prof[i];
   }
   return GRB_OK;
 }

@@ -37,6 +37,10 @@ struct GrbSelState
   uint64_t curr_path;
   grb_path_stats cur;
   grb_path_stats snap; // counters at the last rollover (log_path_stat, :126-154)
+  // k_commit_batch phase clocks of CTA 0 (SM cycles) and event counts, for grb_commit_profile:
+  // 0 check, 1 barrier after check, 2 re-smoothing (+ its barrier), 3 decide, 4 insert,
+  // 5 barrier after insert, 6 reads, 7 reads re-smoothed, 8 reads inserted, 9 reads checked
+  unsigned long long prof[10];
 };
 
 struct GrbSelScratch

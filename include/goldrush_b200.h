@@ -218,12 +218,18 @@ typedef enum grb_kernel_class
   GRB_K_FILL = 0,   /* K2+K4a  k_fill_bits */
   GRB_K_RANK = 1,   /* K4b     k_rank_partial + k_scan_u32 + k_rank_write */
   GRB_K_QUERY = 2,  /* K2+K3   k_spec_query (batch engine) / k_query (serial engine) */
-  GRB_K_DECIDE = 3, /*         k_commit_decide / k_decide */
-  GRB_K_INSERT = 4, /* K4c     k_insert_collect + k_insert_apply */
-  GRB_K_CHECK = 5,  /*         k_commit_check: ordered re-validation of the speculative votes */
-  GRB_K_COUNT = 6
+  GRB_K_DECIDE = 3, /*         k_decide (serial engine) */
+  GRB_K_INSERT = 4, /* K4c     k_insert_collect + k_insert_apply (serial engine) */
+  GRB_K_SMOOTH = 5, /*         k_spec_cmat: count matrix + smoothing on the speculative votes */
+  GRB_K_DEDUPE = 6, /*         k_spec_dedupe: distinct ranks per read for the insert */
+  GRB_K_COMMIT = 7, /* K4c     k_commit_batch: ordered re-validation, decision and insert */
+  GRB_K_COUNT = 8
 } grb_kernel_class;
 int grb_profile_enable(grb_ctx* ctx, int on);
+/* phase clocks of the ordered commit kernel since the last grb_filter_alloc, as counted by its
+ * CTA 0: out[0..5] = SM cycles in check, barrier, re-smoothing, decide, insert, barrier;
+ * out[6..9] = reads committed, re-smoothed, inserted, re-validated. */
+int grb_commit_profile(grb_ctx* ctx, uint64_t* out10);
 int grb_kernel_time(grb_ctx* ctx, int kclass, double* ms, uint64_t* n_launches);
 
 /* ---- whole stage: what goldrush_path.cpp main() does between option parsing and exit ----
