@@ -332,6 +332,20 @@ grb_create(const grb_params* p, grb_ctx** out)
     return bail(GRB_ERR_CUDA, std::string("CUDA init: ") + cudaGetErrorString(e));
   }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+  // The miBF probes are random 32-byte sector reads: ask L2 not to widen them into 64/128-byte
+  // DRAM fetches (a hint; GRB_L2_FETCH=64|128 restores wider fetches for A/B measurements).
+  {
+    size_t gran = 32;
+    if (const char* g = getenv("GRB_L2_FETCH")) {
+      const long v = strtol(g, nullptr, 10);
+      if (v == 32 || v == 64 || v == 128) {
+        gran = (size_t)v;
+      }
+    }
+    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) {
+      cudaGetLastError(); // not fatal: the limit is only a performance hint
+    }
+  }
   // GRB_ENGINE=serial keeps the one-read-at-a-time loop (kernels_select.cuh) for A/B checks;
   // GRB_BATCH_READS overrides the speculative batch size
   if (const char* e = getenv("GRB_ENGINE")) {
