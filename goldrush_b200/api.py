@@ -426,8 +426,8 @@ class Engine:
     def commit_profile(self):
         out = (C.c_uint64 * 10)()
         self._chk(self._L.grb_commit_profile(self._h, out))
-        names = ["check_cyc", "barrier1_cyc", "resmooth_cyc", "decide_cyc", "insert_cyc",
-                 "barrier2_cyc", "reads", "resmoothed", "inserted", "checked"]
+        names = ["check_cyc", "plans_changed", "resmooth_cyc", "decide_cyc", "insert_cyc",
+                 "conflict_frames", "reads", "resmoothed", "inserted", "checked"]
         return dict(zip(names, [int(x) for x in out]))
 
     def kernel_time(self, kclass):

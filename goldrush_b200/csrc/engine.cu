@@ -6,6 +6,7 @@
 #include "kernels_ntcard.cuh"
 #include "kernels_select.cuh"
 #include "kernels_batch.cuh"
+#include "kernels_batch2.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -100,6 +101,18 @@ struct grb_ctx
   uint32_t commit_ctas = 0;
   DevBuf<unsigned long long> bb_barrier;
   DevBuf<uint64_t> bb_dec_idx;
+  // batch engine, second generation (kernels_batch2.cuh)
+  int batch_ver = 2; // GRB_ENGINE=batch1 keeps the grid-wide commit of kernels_batch.cuh
+  uint64_t b2_cap_tiles = 0, b2_ix_entries = 0;
+  uint32_t b2_cap_reads = 0;
+  bool b2_attr = false;
+  size_t b2_smem_max = 0;
+  DevBuf<uint32_t> b2_vk, b2_vc, b2_ix_sidx, b2_counters, b2_c_slot, b2_c_probe, b2_c_next, b2_c_sidx;
+  DevBuf<unsigned long long> b2_ix;
+  DevBuf<GrbShared> b2_shared;
+  DevBuf<uint32_t> b2_fbits, b2_fl_n, b2_fl, b2_fr, b2_rl_n;
+  DevBuf<uint2> b2_rl;
+  DevBuf<GrbReadPlan> b2_plan_out;
 
   // ---- per-kernel-class device timing (grb_profile_enable / grb_kernel_time) ----
   bool prof_on = false;
@@ -350,6 +363,7 @@ grb_create(const grb_params* p, grb_ctx** out)
   // GRB_BATCH_READS overrides the speculative batch size
   if (const char* e = getenv("GRB_ENGINE")) {
     c->batch_mode = strcmp(e, "serial") != 0;
+    c->batch_ver = strcmp(e, "batch1") == 0 ? 1 : 2;
   }
   if (const char* e = getenv("GRB_BATCH_READS")) {
     const long v = strtol(e, nullptr, 10);
@@ -1310,6 +1324,179 @@ launch_batch(grb_ctx* c, const BatchPlan& bp, const BatchPlan::Batch& b, uint64_
   return GRB_OK;
 }
 
+// ---- batch engine, second generation ------------------------------------------------------
+static int
+batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, uint64_t max_cm_words,
+               uint32_t max_batch_reads)
+{
+  cudaStream_t s = c->stream;
+  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  if (max_read_tiles > 2048) {
+    return c->fail(GRB_ERR_ARG, "a read spans more than 2048 tiles: raise the tile length");
+  }
+  if (max_batch_tiles > c->b2_cap_tiles) {
+    const uint64_t n = max_batch_tiles;
+    const uint64_t n_probe = n * T * h;
+    if (n_probe >= (1ull << 26)) {
+      return c->fail(GRB_ERR_ARG, "batch too large for the 26-bit probe index");
+    }
+    c->bb_stash.release();
+    c->b2_vk.release();
+    c->b2_vc.release();
+    c->b2_ix.release();
+    c->b2_ix_sidx.release();
+    GRB_CUDA(c, c->bb_stash.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b2_vk.reserve(n * c->prm.table_size, 0, s));
+    GRB_CUDA(c, c->b2_vc.reserve(n * c->prm.table_size, 0, s));
+    c->b2_ix_entries = next_pow2(n_probe + n_probe / 2);
+    GRB_CUDA(c, c->b2_ix.reserve(c->b2_ix_entries, 0, s));
+    GRB_CUDA(c, c->b2_ix_sidx.reserve(c->b2_ix_entries, 0, s));
+    GRB_CUDA(c, c->b2_c_slot.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b2_c_probe.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b2_c_next.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b2_c_sidx.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b2_shared.reserve(n_probe / 2 + 1, 0, s));
+    GRB_CUDA(c, c->b2_fbits.reserve(n * T / 32 + 2, 0, s));
+    GRB_CUDA(c, c->b2_fl.reserve(n * T, 0, s));
+    GRB_CUDA(c, c->b2_fr.reserve(n * T * (2 + h), 0, s));
+    GRB_CUDA(c, c->b2_rl.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->bb_best_id.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_best_count.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_hits.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_miss.reserve(n, 0, s));
+    GRB_CUDA(c, c->bb_uq.reserve(n, 0, s));
+    GRB_CUDA(c, c->b2_counters.reserve(4, 0, s));
+    c->b2_cap_tiles = n;
+  }
+  if (max_batch_reads > c->b2_cap_reads) {
+    const uint32_t nb = max_batch_reads;
+    GRB_CUDA(c, c->bb_sp_nas.reserve(nb, 0, s));
+    GRB_CUDA(c, c->bb_sp_plan.reserve(nb, 0, s));
+    GRB_CUDA(c, c->bb_sp_adv.reserve(nb, 0, s));
+    GRB_CUDA(c, c->bb_rd_hits.reserve(nb, 0, s));
+    GRB_CUDA(c, c->bb_rd_miss.reserve(nb, 0, s));
+    GRB_CUDA(c, c->bb_rd_q.reserve(nb, 0, s));
+    GRB_CUDA(c, c->bb_nu.reserve(nb, 0, s));
+    GRB_CUDA(c, c->b2_fl_n.reserve(nb, 0, s));
+    GRB_CUDA(c, c->b2_rl_n.reserve(nb, 0, s));
+    GRB_CUDA(c, c->b2_plan_out.reserve(nb, 0, s));
+    c->b2_cap_reads = nb;
+  }
+  GRB_CUDA(c, c->bb_cm.reserve(std::max<uint64_t>(1, max_cm_words), 0, s));
+  if (max_read_tiles > 160) { // count matrix of a very long read spills to global memory
+    GRB_CUDA(c, c->bb_cmat.reserve(max_read_tiles * max_read_tiles, 0, s));
+  }
+  if (!c->b2_attr) {
+    int max_optin = 0;
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+    c->b2_smem_max = (size_t)max_optin - 2048; // static shared memory of the kernels
+    GRB_CUDA(c, cudaFuncSetAttribute(k2_commit<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)c->b2_smem_max));
+    GRB_CUDA(c, cudaFuncSetAttribute(k2_cmat<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)c->b2_smem_max));
+    GRB_CUDA(c, cudaFuncSetAttribute(k2_query<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)c->query_smem));
+    c->b2_attr = true;
+  }
+  return GRB_OK;
+}
+
+static int
+launch_batch2(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
+{
+  cudaStream_t s = c->stream;
+  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  GrbBatchDev bd{};
+  bd.read_idx = c->bb_read_idx.p + b.read0;
+  bd.tile_first = c->bb_tile_first.p + b.tf0;
+  bd.tile_read = c->bb_tile_read.p + b.tr0;
+  bd.nb = b.nb;
+  bd.n_bt = b.n_bt;
+  bd.stash = c->bb_stash.p;
+  bd.best_id = c->bb_best_id.p;
+  bd.best_count = c->bb_best_count.p;
+  bd.tile_hits = c->bb_hits.p;
+  bd.tile_miss = c->bb_miss.p;
+  bd.cmat = c->bb_cmat.p;
+  bd.uq = c->bb_uq.p;
+  bd.nu = c->bb_nu.p;
+  bd.cm = c->bb_cm.p;
+  bd.cm_off = c->bb_cm_off.p + b.read0;
+  bd.sp_n_as = c->bb_sp_nas.p;
+  bd.sp_plan = c->bb_sp_plan.p;
+  bd.sp_adv = c->bb_sp_adv.p;
+  bd.rd_hits = c->bb_rd_hits.p;
+  bd.rd_miss = c->bb_rd_miss.p;
+  bd.rd_queries = c->bb_rd_q.p;
+  GrbB2 b2{};
+  b2.vk = c->b2_vk.p;
+  b2.vc = c->b2_vc.p;
+  b2.table_size = c->prm.table_size;
+  b2.ix_tab = c->b2_ix.p;
+  const uint64_t n_probe = (uint64_t)b.n_bt * T * h;
+  const uint64_t ix_entries = std::min<uint64_t>(c->b2_ix_entries, next_pow2(n_probe + n_probe / 2 + 64));
+  b2.ix_mask = ix_entries - 1;
+  b2.ix_sidx = c->b2_ix_sidx.p;
+  b2.counters = c->b2_counters.p;
+  b2.c_slot = c->b2_c_slot.p;
+  b2.c_probe = c->b2_c_probe.p;
+  b2.c_next = c->b2_c_next.p;
+  b2.c_sidx = c->b2_c_sidx.p;
+  b2.shared = c->b2_shared.p;
+  b2.fbits = c->b2_fbits.p;
+  b2.fl_n = c->b2_fl_n.p;
+  b2.fl = c->b2_fl.p;
+  b2.fr = c->b2_fr.p;
+  b2.rl_n = c->b2_rl_n.p;
+  b2.rl = c->b2_rl.p;
+  b2.plan_out = c->b2_plan_out.p;
+
+  const uint32_t n_cap = std::max<uint32_t>(b.max_tiles, 1);
+  const uint32_t us = (uint32_t)next_pow2(2 * (uint64_t)n_cap);
+  const uint32_t cm_smem = n_cap <= 160 ? 1u : 0u;
+  const size_t as_pad = ((size_t)(n_cap + 15) / 16) * 16;
+  const size_t cmat_smem = (size_t)6 * n_cap * 4 + 8 + (size_t)2 * us * 4 + as_pad +
+                           (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
+  const size_t commit_smem = (size_t)n_cap * 8 + ((size_t)2 * us + (size_t)8 * n_cap + 2) * 4 + as_pad +
+                             (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
+  if (cmat_smem > c->b2_smem_max || commit_smem > c->b2_smem_max) {
+    return c->fail(GRB_ERR_ARG, "a read spans too many tiles for the commit kernel's shared "
+                                "memory: raise the tile length");
+  }
+  GRB_CUDA(c, cudaMemsetAsync(b2.ix_tab, 0xFF, ix_entries * 8, s));
+  GRB_CUDA(c, cudaMemsetAsync(b2.fbits, 0, ((uint64_t)b.n_bt * T / 32 + 2) * 4, s));
+  GRB_CUDA(c, cudaMemsetAsync(b2.counters, 0, 16, s));
+  GRB_CUDA(c, cudaMemsetAsync(b2.fl_n, 0, (size_t)b.nb * 4, s));
+  GRB_CUDA(c, cudaMemsetAsync(b2.rl_n, 0, (size_t)b.nb * 4, s));
+  GRB_CUDA(c, cudaMemsetAsync(b2.plan_out, 0, (size_t)b.nb * sizeof(GrbReadPlan), s));
+  k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
+  c->launches += 1;
+  c->kbegin();
+  k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
+    c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state);
+  c->kend(GRB_K_QUERY);
+  c->kbegin();
+  k2_cmat<256><<<b.nb, 256, cmat_smem, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state, n_cap, us,
+                                           cm_smem);
+  c->kend(GRB_K_SMOOTH);
+  c->kbegin();
+  k2_index<<<grid_for(b.n_bt, 1, 1u << 20), 256, 0, s>>>(c->reads_dev(), c->filt, c->prm, bd, b2,
+                                                         c->d_state);
+  k2_conf<<<c->sm_count * 8, 256, 0, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state);
+  k2_conf2<<<c->sm_count * 8, 256, 0, s>>>(c->reads_dev(), c->filt, c->prm, bd, b2, c->d_state);
+  c->kend(GRB_K_DEDUPE, 3);
+  c->kbegin();
+  k2_commit<1024><<<1, 1024, commit_smem, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state, d_dec,
+                                               c->bb_dec_idx.p + b.read0, us, n_cap, cm_smem);
+  c->kend(GRB_K_COMMIT);
+  c->kbegin();
+  k2_bulk<<<grid_for(b.n_bt, 1, c->sm_count * 16), 256, 0, s>>>(c->reads_dev(), c->filt, c->prm, bd,
+                                                                b2, c->d_state);
+  c->kend(GRB_K_INSERT);
+  GRB_CUDA(c, cudaGetLastError());
+  return GRB_OK;
+}
+
 int
 grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decisions,
                  grb_path_stats* stats, uint32_t stats_cap, uint32_t* n_stats, int* finished)
@@ -1352,13 +1539,19 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       BatchPlan bp;
       const uint64_t T = c->p.tile_length;
       uint64_t max_bt = 0, max_cm = 0, max_dd = 0;
+      uint32_t max_nb = 0;
+      // the second-generation engine indexes a batch's probes with 26 bits
+      const uint64_t tile_budget =
+        c->batch_ver == 2 ? std::max<uint64_t>(1, std::min<uint64_t>(c->batch_tiles,
+                                                                     ((1ull << 26) - 1) / (T * c->h_seed.h)))
+                          : c->batch_tiles;
       for (; j < end && launched < kChunk; ++j) {
         if (!(c->h_flags[j] & GRB_READ_PASS2)) {
           continue;
         }
         const uint32_t tiles = (uint32_t)(c->h_len[j] / T);
         if (bp.batches.empty() || bp.batches.back().nb >= c->batch_reads ||
-            (bp.batches.back().n_bt && bp.batches.back().n_bt + tiles > c->batch_tiles)) {
+            (bp.batches.back().n_bt && bp.batches.back().n_bt + tiles > tile_budget)) {
           if (!bp.batches.empty()) {
             bp.tile_first.push_back(bp.batches.back().n_bt);
           }
@@ -1371,7 +1564,9 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
         bp.dec_idx.push_back(j - first);
         bp.cm_off.push_back(b.cm_words);
         bp.dd_off.push_back(b.dd_entries);
-        const uint64_t dd = (tiles >= 1 && tiles <= 64) ? next_pow2(2ull * tiles * T * c->h_seed.h) : 0;
+        const uint64_t dd = (c->batch_ver == 1 && tiles >= 1 && tiles <= 64)
+                              ? next_pow2(2ull * tiles * T * c->h_seed.h)
+                              : 0;
         bp.dd_size.push_back((uint32_t)dd);
         b.dd_entries += dd;
         max_dd = std::max(max_dd, b.dd_entries);
@@ -1383,11 +1578,15 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
         b.nb += 1;
         b.n_bt += tiles;
         max_bt = std::max<uint64_t>(max_bt, b.n_bt);
+        max_nb = std::max(max_nb, b.nb);
         ++launched;
       }
       if (!bp.batches.empty()) {
         bp.tile_first.push_back(bp.batches.back().n_bt);
-        if ((rc = batch_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_dd)) != GRB_OK) {
+        rc = c->batch_ver == 2
+               ? batch2_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_nb)
+               : batch_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_dd);
+        if (rc != GRB_OK) {
           return rc;
         }
         GRB_CUDA(c, c->bb_read_idx.reserve(bp.read_idx.size(), 0, s));
@@ -1414,7 +1613,9 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
                                       bp.tile_read.size() * 4, cudaMemcpyHostToDevice, s));
         }
         for (const BatchPlan::Batch& b : bp.batches) {
-          if ((rc = launch_batch(c, bp, b, first, c->d_dec.p)) != GRB_OK) {
+          rc = c->batch_ver == 2 ? launch_batch2(c, b, c->d_dec.p)
+                                 : launch_batch(c, bp, b, first, c->d_dec.p);
+          if (rc != GRB_OK) {
             return rc;
           }
         }
@@ -1431,6 +1632,15 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
     GRB_CUDA(c, cudaMemcpyAsync(&st, c->d_state, sizeof st, cudaMemcpyDeviceToHost, s));
     GRB_CUDA(c, cudaStreamSynchronize(s));
     c->kflush();
+    if (st.halt == 2) {
+      // a batch stopped early (vote-table slack exhausted): nothing to reset, start a new batch
+      // at the first read that was not committed
+      st.halt = 0;
+      GRB_CUDA(c, cudaMemcpyAsync(c->d_state, &st, sizeof st, cudaMemcpyHostToDevice, s));
+      GRB_CUDA(c, cudaStreamSynchronize(s));
+      i = st.halt_read;
+      continue;
+    }
     if (st.halt) {
       if (st.n_snap && stats && n_stats && *n_stats < stats_cap) {
         stats[(*n_stats)++] = st.snap;
