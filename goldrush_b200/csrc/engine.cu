@@ -7,6 +7,7 @@
 #include "kernels_select.cuh"
 #include "kernels_batch.cuh"
 #include "kernels_batch2.cuh"
+#include "kernels_fix.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -102,7 +103,7 @@ struct grb_ctx
   DevBuf<unsigned long long> bb_barrier;
   DevBuf<uint64_t> bb_dec_idx;
   // batch engine, second generation (kernels_batch2.cuh)
-  int batch_ver = 2; // GRB_ENGINE=batch1 keeps the grid-wide commit of kernels_batch.cuh
+  int batch_ver = 3; // GRB_ENGINE=batch1 / batch2 keep the earlier commit kernels for A/B runs
   uint64_t b2_cap_tiles = 0, b2_ix_entries = 0;
   uint32_t b2_cap_reads = 0;
   bool b2_attr = false;
@@ -113,6 +114,16 @@ struct grb_ctx
   DevBuf<uint32_t> b2_fbits, b2_fl_n, b2_fl, b2_fr, b2_rl_n;
   DevBuf<uint2> b2_rl;
   DevBuf<GrbReadPlan> b2_plan_out;
+  // third generation (kernels_fix.cuh); shares the b2_* probe-index buffers
+  bool b3_attr = false;
+  uint32_t b3_ctas = 0, b3_dcap = 0;
+  uint64_t b3_cap_tiles = 0, b3_cmat_cap = 0;
+  DevBuf<GrbShared3> b3_shared;
+  DevBuf<uint32_t> b3_c_pos, b3_m_fill, b3_m_key, b3_m_ci, b3_m_seen, b3_np_adv, b3_np_nas, b3_cmat_g;
+  DevBuf<int32_t> b3_np_dh, b3_d_vals;
+  DevBuf<GrbReadPlan> b3_np;
+  DevBuf<GrbFixCtl> b3_ctl;
+  DevBuf<unsigned long long> b3_d_keys, b3_barrier;
 
   // ---- per-kernel-class device timing (grb_profile_enable / grb_kernel_time) ----
   bool prof_on = false;
@@ -363,7 +374,7 @@ grb_create(const grb_params* p, grb_ctx** out)
   // GRB_BATCH_READS overrides the speculative batch size
   if (const char* e = getenv("GRB_ENGINE")) {
     c->batch_mode = strcmp(e, "serial") != 0;
-    c->batch_ver = strcmp(e, "batch1") == 0 ? 1 : 2;
+    c->batch_ver = strcmp(e, "batch1") == 0 ? 1 : (strcmp(e, "batch2") == 0 ? 2 : 3);
   }
   if (const char* e = getenv("GRB_BATCH_READS")) {
     const long v = strtol(e, nullptr, 10);
@@ -1497,6 +1508,188 @@ launch_batch2(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   return GRB_OK;
 }
 
+// ---- batch engine, third generation -------------------------------------------------------
+static const uint32_t kFixDeltaSmem = 8192; // shared-memory delta table entries of k3_fix
+
+static int
+batch3_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, uint64_t max_cm_words,
+               uint32_t max_batch_reads)
+{
+  cudaStream_t s = c->stream;
+  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  int rc = batch2_prepare(c, max_batch_tiles, max_read_tiles, max_cm_words, max_batch_reads);
+  if (rc != GRB_OK) {
+    return rc;
+  }
+  if (max_batch_reads > 1024) {
+    return c->fail(GRB_ERR_ARG, "GRB_BATCH_READS above 1024");
+  }
+  if (!c->b3_attr) {
+    GRB_CUDA(c, cudaFuncSetAttribute(k3_fix<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)c->b2_smem_max));
+    int per_sm = 0;
+    GRB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_fix<512>, 512,
+                                                              c->b2_smem_max));
+    if (per_sm < 1) {
+      return c->fail(GRB_ERR_CUDA, "k3_fix cannot be resident on this device");
+    }
+    c->b3_ctas = (uint32_t)c->sm_count;
+    c->b3_dcap = (uint32_t)next_pow2(4 * T * h + 64);
+    GRB_CUDA(c, c->b3_d_keys.reserve((size_t)c->b3_ctas * c->b3_dcap, 0, s));
+    GRB_CUDA(c, c->b3_d_vals.reserve((size_t)c->b3_ctas * c->b3_dcap, 0, s));
+    GRB_CUDA(c, c->b3_ctl.reserve(1, 0, s));
+    GRB_CUDA(c, c->b3_barrier.reserve(1, 0, s));
+    c->b3_attr = true;
+  }
+  if (max_batch_tiles > c->b3_cap_tiles) {
+    const uint64_t n_probe = max_batch_tiles * T * h;
+    GRB_CUDA(c, c->b3_shared.reserve(n_probe / 2 + 1, 0, s));
+    GRB_CUDA(c, c->b3_m_fill.reserve(n_probe / 2 + 1, 0, s));
+    GRB_CUDA(c, c->b3_c_pos.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b3_m_key.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b3_m_ci.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b3_m_seen.reserve(n_probe, 0, s));
+    c->b2_fr.release();
+    GRB_CUDA(c, c->b2_fr.reserve(max_batch_tiles * T * (2 + 2 * h), 0, s));
+    c->b3_cap_tiles = max_batch_tiles;
+  }
+  GRB_CUDA(c, c->b3_np.reserve(max_batch_reads, 0, s));
+  GRB_CUDA(c, c->b3_np_adv.reserve(max_batch_reads, 0, s));
+  GRB_CUDA(c, c->b3_np_nas.reserve(max_batch_reads, 0, s));
+  GRB_CUDA(c, c->b3_np_dh.reserve(max_batch_reads, 0, s));
+  if (max_read_tiles > 160 && max_read_tiles * max_read_tiles > c->b3_cmat_cap) {
+    c->b3_cmat_cap = max_read_tiles * max_read_tiles;
+    GRB_CUDA(c, c->b3_cmat_g.reserve(c->b3_cmat_cap * c->b3_ctas, 0, s));
+  }
+  return GRB_OK;
+}
+
+static int
+launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
+{
+  cudaStream_t s = c->stream;
+  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  GrbBatchDev bd{};
+  bd.read_idx = c->bb_read_idx.p + b.read0;
+  bd.tile_first = c->bb_tile_first.p + b.tf0;
+  bd.tile_read = c->bb_tile_read.p + b.tr0;
+  bd.nb = b.nb;
+  bd.n_bt = b.n_bt;
+  bd.stash = c->bb_stash.p;
+  bd.best_id = c->bb_best_id.p;
+  bd.best_count = c->bb_best_count.p;
+  bd.tile_hits = c->bb_hits.p;
+  bd.tile_miss = c->bb_miss.p;
+  bd.cmat = c->bb_cmat.p;
+  bd.uq = c->bb_uq.p;
+  bd.nu = c->bb_nu.p;
+  bd.cm = c->bb_cm.p;
+  bd.cm_off = c->bb_cm_off.p + b.read0;
+  bd.sp_n_as = c->bb_sp_nas.p;
+  bd.sp_plan = c->bb_sp_plan.p;
+  bd.sp_adv = c->bb_sp_adv.p;
+  bd.rd_hits = c->bb_rd_hits.p;
+  bd.rd_miss = c->bb_rd_miss.p;
+  bd.rd_queries = c->bb_rd_q.p;
+  GrbB2 b2{};
+  b2.vk = c->b2_vk.p;
+  b2.vc = c->b2_vc.p;
+  b2.table_size = c->prm.table_size;
+  GrbB3 b3{};
+  b3.vk = c->b2_vk.p;
+  b3.vc = c->b2_vc.p;
+  b3.table_size = c->prm.table_size;
+  b3.d_cap = c->b3_dcap;
+  b3.ix_tab = c->b2_ix.p;
+  const uint64_t n_probe = (uint64_t)b.n_bt * T * h;
+  const uint64_t ix_entries = std::min<uint64_t>(c->b2_ix_entries, next_pow2(n_probe + n_probe / 2 + 64));
+  b3.ix_mask = ix_entries - 1;
+  b3.ix_sidx = c->b2_ix_sidx.p;
+  b3.counters = c->b2_counters.p;
+  b3.c_slot = c->b2_c_slot.p;
+  b3.c_probe = c->b2_c_probe.p;
+  b3.c_sidx = c->b2_c_sidx.p;
+  b3.c_pos = c->b3_c_pos.p;
+  b3.shared = c->b3_shared.p;
+  b3.m_fill = c->b3_m_fill.p;
+  b3.m_key = c->b3_m_key.p;
+  b3.m_ci = c->b3_m_ci.p;
+  b3.m_seen = c->b3_m_seen.p;
+  b3.fbits = c->b2_fbits.p;
+  b3.fl_n = c->b2_fl_n.p;
+  b3.fl = c->b2_fl.p;
+  b3.fr = c->b2_fr.p;
+  b3.np = c->b3_np.p;
+  b3.np_adv = c->b3_np_adv.p;
+  b3.np_nas = c->b3_np_nas.p;
+  b3.np_dh = c->b3_np_dh.p;
+  b3.plan_out = c->b2_plan_out.p;
+  b3.ctl = c->b3_ctl.p;
+  b3.d_keys = c->b3_d_keys.p;
+  b3.d_vals = c->b3_d_vals.p;
+  b3.cmat_g = c->b3_cmat_g.p;
+  b3.barrier = c->b3_barrier.p;
+
+  const uint32_t n_cap = std::max<uint32_t>(b.max_tiles, 1);
+  const uint32_t us = (uint32_t)next_pow2(2 * (uint64_t)n_cap);
+  const uint32_t cm_smem = n_cap <= 160 ? 1u : 0u;
+  const size_t as_pad = ((size_t)(n_cap + 15) / 16) * 16;
+  const size_t cmat_smem = (size_t)6 * n_cap * 4 + 8 + (size_t)2 * us * 4 + as_pad +
+                           (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
+  const uint32_t dc = kFixDeltaSmem;
+  const size_t fix_smem = (size_t)dc * 12 + (size_t)n_cap * 8 + ((size_t)2 * us + (size_t)8 * n_cap + 2) * 4 +
+                          as_pad + (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
+  if (cmat_smem > c->b2_smem_max || fix_smem > c->b2_smem_max) {
+    return c->fail(GRB_ERR_ARG, "a read spans too many tiles for the commit kernel's shared "
+                                "memory: raise the tile length");
+  }
+  GRB_CUDA(c, cudaMemsetAsync(b3.ix_tab, 0xFF, ix_entries * 8, s));
+  GRB_CUDA(c, cudaMemsetAsync(b3.fbits, 0, ((uint64_t)b.n_bt * T / 32 + 2) * 4, s));
+  GRB_CUDA(c, cudaMemsetAsync(b3.counters, 0, 16, s));
+  GRB_CUDA(c, cudaMemsetAsync(b3.fl_n, 0, (size_t)b.nb * 4, s));
+  GRB_CUDA(c, cudaMemsetAsync(b3.plan_out, 0, (size_t)b.nb * sizeof(GrbReadPlan), s));
+  GRB_CUDA(c, cudaMemsetAsync(b3.ctl, 0, sizeof(GrbFixCtl), s));
+  GRB_CUDA(c, cudaMemsetAsync(b3.barrier, 0, 8, s));
+  k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
+  c->launches += 1;
+  c->kbegin();
+  k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
+    c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state);
+  c->kend(GRB_K_QUERY);
+  c->kbegin();
+  k2_cmat<256><<<b.nb, 256, cmat_smem, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state, n_cap, us,
+                                           cm_smem);
+  c->kend(GRB_K_SMOOTH);
+  c->kbegin();
+  const unsigned g_small = (unsigned)c->sm_count * 8;
+  k3_index<<<grid_for(b.n_bt, 1, 1u << 20), 256, 0, s>>>(c->reads_dev(), c->filt, c->prm, bd, b3,
+                                                         c->d_state);
+  k3_conf<<<g_small, 256, 0, s>>>(c->reads_dev(), c->prm, bd, b3, c->d_state);
+  k3_seg<<<g_small, 256, 0, s>>>(b3, c->d_state);
+  k3_scatter<<<g_small, 256, 0, s>>>(c->prm, bd, b3, c->d_state);
+  k3_sort<<<g_small, 256, 0, s>>>(b3, c->d_state);
+  k3_frames<<<grid_for(b.nb, 1, g_small), 256, 0, s>>>(c->filt, c->prm, bd, b3, c->d_state);
+  c->kend(GRB_K_DEDUPE, 6);
+  {
+    GrbReadsDev reads = c->reads_dev();
+    GrbSelState* st = c->d_state;
+    grb_decision* dec = d_dec;
+    const uint64_t* dec_idx = c->bb_dec_idx.p + b.read0;
+    uint32_t us_a = us, n_cap_a = n_cap, dc_a = dc, cm_a = cm_smem;
+    void* args[] = { &reads, &c->prm, &bd, &b3, &st, &dec, &dec_idx, &us_a, &n_cap_a, &dc_a, &cm_a };
+    c->kbegin();
+    GRB_CUDA(c, cudaLaunchCooperativeKernel((void*)k3_fix<512>, dim3(c->b3_ctas), dim3(512), args,
+                                            fix_smem, s));
+    c->kend(GRB_K_COMMIT);
+  }
+  c->kbegin();
+  k3_bulk<<<grid_for(b.n_bt, 1, c->sm_count * 16), 256, 0, s>>>(c->reads_dev(), c->filt, c->prm, bd,
+                                                                b3, c->d_state);
+  c->kend(GRB_K_INSERT);
+  GRB_CUDA(c, cudaGetLastError());
+  return GRB_OK;
+}
+
 int
 grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decisions,
                  grb_path_stats* stats, uint32_t stats_cap, uint32_t* n_stats, int* finished)
@@ -1542,7 +1735,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       uint32_t max_nb = 0;
       // the second-generation engine indexes a batch's probes with 26 bits
       const uint64_t tile_budget =
-        c->batch_ver == 2 ? std::max<uint64_t>(1, std::min<uint64_t>(c->batch_tiles,
+        c->batch_ver >= 2 ? std::max<uint64_t>(1, std::min<uint64_t>(c->batch_tiles,
                                                                      ((1ull << 26) - 1) / (T * c->h_seed.h)))
                           : c->batch_tiles;
       for (; j < end && launched < kChunk; ++j) {
@@ -1583,9 +1776,11 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       }
       if (!bp.batches.empty()) {
         bp.tile_first.push_back(bp.batches.back().n_bt);
-        rc = c->batch_ver == 2
-               ? batch2_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_nb)
-               : batch_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_dd);
+        rc = c->batch_ver == 3
+               ? batch3_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_nb)
+               : c->batch_ver == 2
+                   ? batch2_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_nb)
+                   : batch_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_dd);
         if (rc != GRB_OK) {
           return rc;
         }
@@ -1613,8 +1808,9 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
                                       bp.tile_read.size() * 4, cudaMemcpyHostToDevice, s));
         }
         for (const BatchPlan::Batch& b : bp.batches) {
-          rc = c->batch_ver == 2 ? launch_batch2(c, b, c->d_dec.p)
-                                 : launch_batch(c, bp, b, first, c->d_dec.p);
+          rc = c->batch_ver == 3 ? launch_batch3(c, b, c->d_dec.p)
+               : c->batch_ver == 2 ? launch_batch2(c, b, c->d_dec.p)
+                                   : launch_batch(c, bp, b, first, c->d_dec.p);
           if (rc != GRB_OK) {
             return rc;
           }

@@ -368,8 +368,9 @@ def test_batch_engine_equals_serial_engine(shape):
                   ratio=shape["ratio"], threshold=shape["threshold"], hash_num=shape["hash_num"])
     ref = _select_all(data, {"GRB_ENGINE": "serial"}, **dict(params))
     assert any(d[0] in (2, 3) for d in ref[0]) and any(d[0] == 4 for d in ref[0])
-    for b in ("1", "3", "32", "128"):
-        got = _select_all(data, {"GRB_ENGINE": "batch", "GRB_BATCH_READS": b}, **dict(params))
+    for eng, b in (("batch", "1"), ("batch", "3"), ("batch", "32"), ("batch", "128"),
+                   ("batch", "512"), ("batch2", "32")):
+        got = _select_all(data, {"GRB_ENGINE": eng, "GRB_BATCH_READS": b}, **dict(params))
         assert got[0] == ref[0], b
         assert got[1] == ref[1], b
         assert got[2] == ref[2], b
