@@ -12,11 +12,13 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fcntl.h>
 #include <string>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <thread>
 #include <unistd.h>
 #include <unordered_set>
 #include <vector>
@@ -62,14 +64,6 @@ struct OutFile
       f = fopen(path.c_str(), "wb");
     }
   }
-  void put(const char* p, size_t n)
-  {
-    if (f) {
-      fwrite(p, 1, n, f);
-    }
-    digest->add(p, n);
-  }
-  void put(const std::string& s) { put(s.data(), s.size()); }
   void close()
   {
     if (f) {
@@ -139,6 +133,15 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
              char* err, size_t err_cap)
 {
   const double t_wall0 = now_ms();
+  const bool timing = getenv("GRB_TIMING") != nullptr; // host-side phase clock on stderr
+  double t_mark = t_wall0;
+  auto mark = [&](const char* what) {
+    if (timing) {
+      const double t = now_ms();
+      fprintf(stderr, "[grb timing] %-12s %9.1f ms\n", what, t - t_mark);
+      t_mark = t;
+    }
+  };
   grb_run_result R{};
   const Log log{ !o->quiet };
   grb_params p = o->params;
@@ -239,6 +242,7 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
       off += used;
     }
   }
+  mark("create+ingest");
   const uint64_t nreads = grb_reads_count(ctx);
   std::vector<grb_read_meta> meta(nreads);
   if (nreads && (rc = grb_reads_get_meta(ctx, 0, nreads, meta.data())) != GRB_OK) {
@@ -362,6 +366,7 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
   }
   R.num_passed_reads = passed;
 
+  mark("filters");
   log("allocating bit vector\n");
   const uint64_t filter_bits = grb_calc_optimal_size(p.hash_universe, 1, p.occupancy);
   log("m_filterSize: %llu\n", (unsigned long long)filter_bits);
@@ -405,6 +410,7 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
   R.ms_rank = grb_last_device_ms(ctx);
   R.pop = pop;
 
+  mark("pass1+rank");
   // ---- pass 2 ----
   log("assigning tiles\n");
   std::vector<grb_decision> dec(nreads);
@@ -422,10 +428,69 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
     return fail(rc);
   }
 
+  mark("pass2");
   // ---- outputs (goldrush_path.cpp:973-976,996-1002,1055-1070,1174-1179,182-184) ----
+  // Pass A (serial, O(#reads)): which records go where.  Pass B (parallel over records, chunked):
+  // assemble the record bytes.  Pass C (serial, in record order): write, digest, path log lines.
   double tab[256];
   for (int b = 0; b < 256; ++b) {
     tab[b] = pow(10.0, -(int)((char)b - 33) / 10.0);
+  }
+  struct Rec
+  {
+    uint64_t read;
+    size_t s0, sl, ql;
+    size_t at, bytes;   // position inside the chunk buffer
+    uint32_t id_len;
+    bool trimmed, closes_path;
+    double phred;
+    uint64_t hash;
+  };
+  std::vector<Rec> recs;
+  const uint64_t T = p.tile_length;
+  uint64_t visited_reads = 0;
+  {
+    uint32_t snap_i = 0;
+    for (uint64_t i = 0; i < nreads; ++i) {
+      const grb_decision& d = dec[i];
+      if (d.verdict == GRB_NOT_VISITED) {
+        break;
+      }
+      ++visited_reads;
+      if (d.verdict != GRB_SKIPPED) {
+        ++R.reads_visited;
+        R.bases_pass2 += (uint64_t)d.num_tiles * T;
+      }
+      if (d.verdict != GRB_UNTRIMMED && d.verdict != GRB_TRIMMED) {
+        continue;
+      }
+      Rec r{};
+      r.read = i;
+      r.trimmed = d.verdict == GRB_TRIMMED;
+      r.s0 = 0;
+      r.sl = meta[i].len;
+      if (r.trimmed) {
+        r.s0 = (size_t)d.trim_start * T;
+        r.sl = (d.trim_end == d.num_tiles - 1) ? meta[i].len - r.s0
+                                               : (size_t)(d.trim_end - d.trim_start + 1) * T;
+      }
+      r.ql = std::min<size_t>(r.sl, meta[i].qual_len > r.s0 ? meta[i].qual_len - r.s0 : 0);
+      const char* hdr = data + meta[i].hdr_off;
+      uint32_t l = 0;
+      while (l < meta[i].hdr_len && hdr[l] != ' ' && hdr[l] != '\t') {
+        ++l;
+      }
+      r.id_len = l;
+      r.bytes = 1 + l + (r.trimmed ? 9 : 11) + r.sl + 1 + (p.silver_path ? 2 + r.ql + 1 : 0);
+      // silver_path_check (goldrush_path.cpp:156-187): a snapshot was taken right after this read
+      r.closes_path = snap_i < n_snaps && snaps[snap_i].rollover_read == i;
+      if (r.closes_path) {
+        ++snap_i;
+      }
+      recs.push_back(r);
+      ++R.reads_selected;
+      R.bases_selected += r.sl;
+    }
   }
   Fnv digest;
   OutFile out;
@@ -436,51 +501,85 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
   const char first_char = p.silver_path ? '@' : '>';
   uint32_t path_now = 1, snap_i = 0;
   double phred_sum = 0;
-  uint64_t processed = 1; // the reference's `id` counter (goldrush_path.cpp:1225)
-  const uint64_t T = p.tile_length;
-  for (uint64_t i = 0; i < nreads; ++i) {
-    const grb_decision& d = dec[i];
-    if (d.verdict == GRB_NOT_VISITED) {
-      break;
+  const bool want_phred = !o->quiet && o->verbose;
+  const bool want_bytes = out.write;
+  int n_threads = o->jobs > 0 ? o->jobs : (int)std::max(1u, std::thread::hardware_concurrency());
+  n_threads = std::min(n_threads, 64);
+  std::vector<char> buf;
+  const size_t kChunkBytes = (size_t)512 << 20;
+  size_t r0 = 0;
+  while (r0 < recs.size()) {
+    size_t r1 = r0, bytes = 0;
+    while (r1 < recs.size() && (r1 == r0 || bytes + recs[r1].bytes <= kChunkBytes)) {
+      recs[r1].at = bytes;
+      bytes += recs[r1].bytes;
+      ++r1;
     }
-    if (d.verdict != GRB_SKIPPED) {
-      ++R.reads_visited;
-      R.bases_pass2 += (uint64_t)d.num_tiles * T;
+    if (want_bytes && buf.size() < bytes) {
+      buf.resize(bytes);
     }
-    if (d.verdict == GRB_UNTRIMMED || d.verdict == GRB_TRIMMED) {
-      if (d.path != path_now) { // a rollover happened right after the previous selected read
-        path_now = d.path;
+#pragma omp parallel num_threads(n_threads)
+    {
+      std::vector<char> local; // record scratch when nothing is written (digest only)
+#pragma omp for schedule(dynamic, 4)
+      for (int64_t ri = (int64_t)r0; ri < (int64_t)r1; ++ri) {
+        Rec& r = recs[ri];
+        const grb_read_meta& m = meta[r.read];
+        char* dst;
+        if (want_bytes) {
+          dst = buf.data() + r.at;
+        } else {
+          if (local.size() < r.bytes) {
+            local.resize(r.bytes);
+          }
+          dst = local.data();
+        }
+        char* w = dst;
+        *w++ = first_char;
+        memcpy(w, data + m.hdr_off, r.id_len);
+        w += r.id_len;
+        if (r.trimmed) {
+          memcpy(w, "_trimmed\n", 9);
+          w += 9;
+        } else {
+          memcpy(w, "_untrimmed\n", 11);
+          w += 11;
+        }
+        const char* sq = data + m.seq_off + r.s0;
+        for (size_t j = 0; j < r.sl; ++j) { // SeqReader folds the sequence to upper case
+          const unsigned char ch = (unsigned char)sq[j];
+          w[j] = (char)(ch - (((unsigned)(ch - 'a') < 26u) << 5));
+        }
+        w += r.sl;
+        *w++ = '\n';
+        const char* ql = data + m.qual_off + r.s0;
+        if (p.silver_path) {
+          *w++ = '+';
+          *w++ = '\n';
+          memcpy(w, ql, r.ql);
+          w += r.ql;
+          *w++ = '\n';
+        }
+        Fnv hsh;
+        hsh.add(dst, r.bytes);
+        r.hash = hsh.h;
+        // the reference adds sum_phred of the written quality string (goldrush_path.cpp:1005-1008);
+        // for a whole read that is the running sum the device already holds
+        r.phred = 0;
+        if (want_phred) {
+          r.phred = (!r.trimmed && r.ql == m.qual_len) ? m.phred_total_sum : sum_phred_host(ql, r.ql, tab);
+        }
       }
-      const std::string id = read_id(i);
-      size_t s0 = 0, sl = meta[i].len;
-      if (d.verdict == GRB_TRIMMED) {
-        s0 = (size_t)d.trim_start * T;
-        sl = (d.trim_end == d.num_tiles - 1) ? meta[i].len - s0
-                                             : (size_t)(d.trim_end - d.trim_start + 1) * T;
+    }
+    for (size_t ri = r0; ri < r1; ++ri) {
+      const Rec& r = recs[ri];
+      if (out.f) {
+        fwrite(buf.data() + r.at, 1, r.bytes, out.f);
       }
-      std::string rec;
-      rec.reserve(2 * sl + id.size() + 32);
-      rec.push_back(first_char);
-      rec += id;
-      rec += d.verdict == GRB_TRIMMED ? "_trimmed\n" : "_untrimmed\n";
-      const size_t seq_at = rec.size();
-      rec.append(data + meta[i].seq_off + s0, sl);
-      for (size_t j = seq_at; j < rec.size(); ++j) { // SeqReader folds the sequence to upper case
-        rec[j] = (char)toupper((unsigned char)rec[j]);
-      }
-      rec.push_back('\n');
-      const size_t ql = std::min<size_t>(sl, meta[i].qual_len > s0 ? meta[i].qual_len - s0 : 0);
-      if (p.silver_path) {
-        rec += "+\n";
-        rec.append(data + meta[i].qual_off + s0, ql);
-        rec.push_back('\n');
-      }
-      out.put(rec);
-      ++R.reads_selected;
-      R.bases_selected += sl;
-      phred_sum += sum_phred_host(data + meta[i].qual_off + s0, ql, tab);
-      // silver_path_check (goldrush_path.cpp:156-187): a snapshot was taken right after this read
-      if (snap_i < n_snaps && snaps[snap_i].rollover_read == i) {
+      digest.add((const char*)&r.hash, 8);
+      phred_sum += r.phred;
+      path_now = dec[r.read].path;
+      if (r.closes_path) {
         if (o->verbose) {
           log_path_stat(log, path_now, snaps[snap_i], phred_sum);
         }
@@ -491,12 +590,13 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
         }
       }
     }
-    ++processed;
-    if (processed % 10000 == 0) {
-      log("processed %llu reads\n", (unsigned long long)processed);
-    }
+    r0 = r1;
+  }
+  for (uint64_t done = 10000; done <= visited_reads + 1; done += 10000) {
+    log("processed %llu reads\n", (unsigned long long)done);
   }
   out.close();
+  mark("outputs");
   R.paths = (uint32_t)curr_path;
   if (!finished) {
     if (p.silver_path && p.max_paths > curr_path) { // goldrush_path.cpp:1257-1264

@@ -270,7 +270,7 @@ typedef struct grb_run_result
   double ms_pass2;
   double ms_wall;             /* host wall clock of the whole call */
   uint64_t launches;
-  uint64_t out_digest;        /* FNV-1a over the bytes the output files hold (also when not written) */
+  uint64_t out_digest;        /* FNV-1a over the per-record FNV-1a hashes of the output records, in output order (also when nothing is written) */
 } grb_run_result;
 
 int grb_run_path(const grb_run_options* opt, const char* fastq, size_t fastq_len,

@@ -11,8 +11,8 @@ if [[ " $* " != *" notest "* ]]; then
   tail -5 $OUT/pytest_$TAG.log
 fi
 if [[ " $* " != *" nobench "* ]]; then
-  timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
-  echo "bench exit $?"; tail -c 3000 $OUT/bench_$TAG.json; tail -5 $OUT/bench_$TAG.err
+  GRB_TIMING=1 timeout 900 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+  echo "bench exit $?"; tail -c 3000 $OUT/bench_$TAG.json; tail -12 $OUT/bench_$TAG.err
 fi
 if [[ " $* " == *" ncu "* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
