@@ -39,10 +39,16 @@ $(ROOT)build/grb-synth: $(ROOT)goldrush_b200/host/synth.cpp $(ROOT)goldrush_b200
 	@mkdir -p $(ROOT)build
 	$(GRB_CXX) $(CXXFLAGS_HOST) -o $@ $(ROOT)goldrush_b200/host/synth.cpp $(ROOT)goldrush_b200/host/grb_synth_main.cpp
 
+tools: $(ROOT)build/sector-roofline
+
+$(ROOT)build/sector-roofline: $(ROOT)tools/sector_roofline.cu
+	@mkdir -p $(ROOT)build
+	$(NVCC) -O3 -gencode arch=compute_100a,code=sm_100a -o $@ $<
+
 oracle:
 	$(MAKE) -C $(ROOT)oracle all
 
 clean:
 	rm -rf $(ROOT)build $(LIBDIR)
 
-.PHONY: all lib goldrush-path host-tools oracle clean
+.PHONY: all lib goldrush-path host-tools tools oracle clean

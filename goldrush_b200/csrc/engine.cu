@@ -62,6 +62,7 @@ struct grb_ctx
   // ---- filter ----
   GrbFilterDev filt{};
   bool filter_alloc = false, finalized = false;
+  uint64_t blocks_cap = 0, slots_cap = 0; // bytes allocated behind filt.blocks / filt.slots
   DevBuf<uint32_t> d_chunk_read;
   DevBuf<uint64_t> d_chunk_first;
 
@@ -119,6 +120,8 @@ struct grb_ctx
   uint32_t b3_ctas = 0, b3_dcap = 0;
   uint64_t b3_cap_tiles = 0, b3_cmat_cap = 0;
   DevBuf<GrbShared3> b3_shared;
+  DevBuf<uint32_t> b3_bm, b3_cand, b3_ix_cnt;
+  uint32_t b3_bm_bits = 0;
   DevBuf<uint32_t> b3_c_pos, b3_m_fill, b3_m_key, b3_m_ci, b3_m_seen, b3_np_adv, b3_np_nas, b3_cmat_g;
   DevBuf<int32_t> b3_np_dh, b3_d_vals;
   DevBuf<GrbReadPlan> b3_np;
@@ -356,18 +359,16 @@ grb_create(const grb_params* p, grb_ctx** out)
     return bail(GRB_ERR_CUDA, std::string("CUDA init: ") + cudaGetErrorString(e));
   }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
-  // The miBF probes are random 32-byte sector reads: ask L2 not to widen them into 64/128-byte
-  // DRAM fetches (a hint; GRB_L2_FETCH=64|128 restores wider fetches for A/B measurements).
-  {
-    size_t gran = 32;
-    if (const char* g = getenv("GRB_L2_FETCH")) {
-      const long v = strtol(g, nullptr, 10);
-      if (v == 32 || v == 64 || v == 128) {
-        gran = (size_t)v;
+  // L2 -> DRAM fetch granularity: measured on B200 (profiles/sector_roofline_r01.json, ncu
+  // dram__sectors_read of k2_query) every L2 miss moves a whole 128-byte line whatever this limit
+  // says, and asking for 32 bytes only slowed the L2-sized structures down.  The device default is
+  // kept; GRB_L2_FETCH=32|64|128 sets the limit for A/B measurements.
+  if (const char* g = getenv("GRB_L2_FETCH")) {
+    const long v = strtol(g, nullptr, 10);
+    if (v == 32 || v == 64 || v == 128) {
+      if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v) != cudaSuccess) {
+        cudaGetLastError(); // not fatal: the limit is only a performance hint
       }
-    }
-    if (cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran) != cudaSuccess) {
-      cudaGetLastError(); // not fatal: the limit is only a performance hint
     }
   }
   // GRB_ENGINE=serial keeps the one-read-at-a-time loop (kernels_select.cuh) for A/B checks;
@@ -735,19 +736,21 @@ grb_filter_alloc(grb_ctx* c, uint64_t filter_bits)
   if (filter_bits < 64) {
     return c->fail(GRB_ERR_ARG, "grb_filter_alloc: filter smaller than 64 bits");
   }
-  if (c->filt.blocks) {
-    cudaFree(c->filt.blocks);
-    c->filt.blocks = nullptr;
-  }
-  if (c->filt.slots) {
-    cudaFree(c->filt.slots);
-    c->filt.slots = nullptr;
-  }
   c->filt.bits = filter_bits;
   c->filt.inv = (uint64_t)((((__uint128_t)1) << 64) / filter_bits);
   c->filt.n_blocks = (filter_bits + GRB_BLK_BITS - 1) / GRB_BLK_BITS;
   c->filt.pop = 0;
-  GRB_CUDA(c, cudaMalloc(&c->filt.blocks, c->filt.n_blocks * 32));
+  // device allocations are kept across runs of one context (cudaMalloc / cudaFree of tens of GB
+  // cost more than the rank build)
+  if (c->filt.n_blocks * 32 > c->blocks_cap) {
+    if (c->filt.blocks) {
+      cudaFree(c->filt.blocks);
+      c->filt.blocks = nullptr;
+      c->blocks_cap = 0;
+    }
+    GRB_CUDA(c, cudaMalloc(&c->filt.blocks, c->filt.n_blocks * 32));
+    c->blocks_cap = c->filt.n_blocks * 32;
+  }
   GRB_CUDA(c, cudaMemsetAsync(c->filt.blocks, 0, c->filt.n_blocks * 32, c->stream));
   c->filter_alloc = true;
   c->finalized = false;
@@ -835,7 +838,15 @@ grb_finalize_bitvector(grb_ctx* c, uint64_t* pop)
   GRB_CUDA(c, cudaGetLastError());
   c->filt.pop = total;
   // m_data + m_counts (MIBloomFilter.hpp:165-184, MIBFConstructSupport.hpp:175-181), zeroed
-  GRB_CUDA(c, cudaMalloc(&c->filt.slots, (total + 1) * sizeof(GrbSlot)));
+  if ((total + 1) * sizeof(GrbSlot) > c->slots_cap) {
+    if (c->filt.slots) {
+      cudaFree(c->filt.slots);
+      c->filt.slots = nullptr;
+      c->slots_cap = 0;
+    }
+    GRB_CUDA(c, cudaMalloc(&c->filt.slots, (total + 1) * sizeof(GrbSlot)));
+    c->slots_cap = (total + 1) * sizeof(GrbSlot);
+  }
   GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, (total + 1) * sizeof(GrbSlot), s));
   GRB_CUDA(c, cudaStreamSynchronize(s));
   c->finalized = true;
@@ -1376,7 +1387,7 @@ batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
     GRB_CUDA(c, c->bb_hits.reserve(n, 0, s));
     GRB_CUDA(c, c->bb_miss.reserve(n, 0, s));
     GRB_CUDA(c, c->bb_uq.reserve(n, 0, s));
-    GRB_CUDA(c, c->b2_counters.reserve(4, 0, s));
+    GRB_CUDA(c, c->b2_counters.reserve(8, 0, s));
     c->b2_cap_tiles = n;
   }
   if (max_batch_reads > c->b2_cap_reads) {
@@ -1546,6 +1557,12 @@ batch3_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
     GRB_CUDA(c, c->b3_shared.reserve(n_probe / 2 + 1, 0, s));
     GRB_CUDA(c, c->b3_m_fill.reserve(n_probe / 2 + 1, 0, s));
     GRB_CUDA(c, c->b3_c_pos.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b3_cand.reserve(n_probe, 0, s));
+    GRB_CUDA(c, c->b3_ix_cnt.reserve(c->b2_ix_entries, 0, s));
+    // rank bit map of a batch: 32 bits per probe keeps the false-positive share near 3 %, and
+    // 2^28 bits (32 MB) is what stays resident in L2 next to the streams
+    c->b3_bm_bits = (uint32_t)std::min<uint64_t>(1ull << 28, next_pow2(32 * n_probe));
+    GRB_CUDA(c, c->b3_bm.reserve(c->b3_bm_bits / 32 + 1, 0, s));
     GRB_CUDA(c, c->b3_m_key.reserve(n_probe, 0, s));
     GRB_CUDA(c, c->b3_m_ci.reserve(n_probe, 0, s));
     GRB_CUDA(c, c->b3_m_seen.reserve(n_probe, 0, s));
@@ -1601,12 +1618,18 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   b3.table_size = c->prm.table_size;
   b3.d_cap = c->b3_dcap;
   b3.ix_tab = c->b2_ix.p;
+  b3.bm = c->b3_bm.p;
+  b3.cand = c->b3_cand.p;
+  b3.ix_cnt = c->b3_ix_cnt.p;
+  b3.t_probe = c->b2_c_next.p;
+  b3.t_slot = c->b2_c_slot.p;
   const uint64_t n_probe = (uint64_t)b.n_bt * T * h;
+  const uint32_t bm_bits = (uint32_t)std::min<uint64_t>(c->b3_bm_bits, std::max<uint64_t>(1024, next_pow2(32 * n_probe)));
+  b3.bm_mask = bm_bits - 1;
   const uint64_t ix_entries = std::min<uint64_t>(c->b2_ix_entries, next_pow2(n_probe + n_probe / 2 + 64));
   b3.ix_mask = ix_entries - 1;
   b3.ix_sidx = c->b2_ix_sidx.p;
   b3.counters = c->b2_counters.p;
-  b3.c_slot = c->b2_c_slot.p;
   b3.c_probe = c->b2_c_probe.p;
   b3.c_sidx = c->b2_c_sidx.p;
   b3.c_pos = c->b3_c_pos.p;
@@ -1643,9 +1666,9 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
     return c->fail(GRB_ERR_ARG, "a read spans too many tiles for the commit kernel's shared "
                                 "memory: raise the tile length");
   }
-  GRB_CUDA(c, cudaMemsetAsync(b3.ix_tab, 0xFF, ix_entries * 8, s));
+  GRB_CUDA(c, cudaMemsetAsync(b3.bm, 0, (size_t)bm_bits / 8, s));
   GRB_CUDA(c, cudaMemsetAsync(b3.fbits, 0, ((uint64_t)b.n_bt * T / 32 + 2) * 4, s));
-  GRB_CUDA(c, cudaMemsetAsync(b3.counters, 0, 16, s));
+  GRB_CUDA(c, cudaMemsetAsync(b3.counters, 0, 32, s));
   GRB_CUDA(c, cudaMemsetAsync(b3.fl_n, 0, (size_t)b.nb * 4, s));
   GRB_CUDA(c, cudaMemsetAsync(b3.plan_out, 0, (size_t)b.nb * sizeof(GrbReadPlan), s));
   GRB_CUDA(c, cudaMemsetAsync(b3.ctl, 0, sizeof(GrbFixCtl), s));
@@ -1662,14 +1685,18 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   c->kend(GRB_K_SMOOTH);
   c->kbegin();
   const unsigned g_small = (unsigned)c->sm_count * 8;
-  k3_index<<<grid_for(b.n_bt, 1, 1u << 20), 256, 0, s>>>(c->reads_dev(), c->filt, c->prm, bd, b3,
-                                                         c->d_state);
+  const unsigned g_tiles = grid_for(b.n_bt, 1, (unsigned)c->sm_count * 8);
+  k3_mark<<<g_tiles, 256, 0, s>>>(c->reads_dev(), c->prm, bd, b3, c->d_state);
+  k3_set_clear<<<g_small, 256, 0, s>>>(b3, c->d_state);
+  k3_dupset<<<g_small, 256, 0, s>>>(bd, b3, c->d_state);
+  k3_members<<<g_tiles, 256, 0, s>>>(c->reads_dev(), c->prm, bd, b3, c->d_state);
+  k3_open<<<g_small, 256, 0, s>>>(c->filt, b3, c->d_state);
   k3_conf<<<g_small, 256, 0, s>>>(c->reads_dev(), c->prm, bd, b3, c->d_state);
   k3_seg<<<g_small, 256, 0, s>>>(b3, c->d_state);
   k3_scatter<<<g_small, 256, 0, s>>>(c->prm, bd, b3, c->d_state);
   k3_sort<<<g_small, 256, 0, s>>>(b3, c->d_state);
   k3_frames<<<grid_for(b.nb, 1, g_small), 256, 0, s>>>(c->filt, c->prm, bd, b3, c->d_state);
-  c->kend(GRB_K_DEDUPE, 6);
+  c->kend(GRB_K_DEDUPE, 10);
   {
     GrbReadsDev reads = c->reads_dev();
     GrbSelState* st = c->d_state;

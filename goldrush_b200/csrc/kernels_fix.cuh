@@ -50,12 +50,17 @@ struct GrbB3
   uint32_t* vc;
   uint32_t table_size;
   uint32_t d_cap;             // per-CTA global delta table entries (power of two)
-  unsigned long long* ix_tab; // batch index: rank << 27 | probe << 1 | shared flag
-  uint64_t ix_mask;
-  uint32_t* ix_sidx;  // per index slot: shared-table index once flagged
-  uint32_t* counters; // [0] conflicts, [1] shared ranks, [2] member cursor
-  uint32_t* c_slot;   // per conflict: index slot, probe (stash index), shared index, member position
-  uint32_t* c_probe;
+  uint32_t* bm;               // rank bit map of the batch, bm_mask + 1 bits
+  uint32_t bm_mask;
+  uint32_t* cand;             // probes whose bit was already set
+  unsigned long long* ix_tab; // exact set of the candidates' ranks (GRB_IX_EMPTY = free)
+  uint64_t ix_mask;           // capacity - 1; the part in use follows the candidate count
+  uint32_t* ix_cnt;   // per set slot: probes of the batch with that rank
+  uint32_t* ix_sidx;  // per set slot: shared-table index (count >= 2)
+  uint32_t* counters; // GRB_CTR_*
+  uint32_t* t_probe;  // probes found in the set, and their set slot
+  uint32_t* t_slot;
+  uint32_t* c_probe;  // per conflict: probe (stash index), shared index, member position
   uint32_t* c_sidx;
   uint32_t* c_pos;
   GrbShared3* shared;
@@ -81,67 +86,224 @@ struct GrbB3
 
 // ---------------------------------------------------------------------------------------------
 // batch index and conflict bookkeeping
+//
+// Which ranks are probed more than once in this batch?  A 64-bit CAS table over all ~10^7 probes is
+// larger than L2 and ran at a third of the device's atomic rate, so the question is answered in
+// three L2-resident steps:
+//   k3_mark     every valid probe sets bit mix(rank) of a 2^28-bit map (32 MB); a probe that finds
+//               its bit already set is a CANDIDATE (a later duplicate, or a false positive)
+//   k3_dupset   the candidates' ranks enter a small exact hash set (a few MB)
+//   k3_members  every valid probe looks its rank up in the set; the probes found are counted per
+//               rank and listed.  A rank counted twice or more is shared, the others were false
+//               positives of the bit map and stay private.
+//   k3_open     one shared entry per rank counted >= 2
+//   k3_conf     the listed probes of shared ranks become the conflict list (as before)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k3_index(GrbReadsDev reads, GrbFilterDev filt, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
-         const GrbSelState* __restrict__ state)
+#define GRB_CTR_CONF 0   // conflicts
+#define GRB_CTR_SHARED 1 // shared ranks
+#define GRB_CTR_MEMBER 2 // member cursor
+#define GRB_CTR_CAND 3   // candidates of k3_mark
+#define GRB_CTR_LISTED 4 // probes listed by k3_members
+
+// append `item` (when `take`) to a global list with one atomic per CTA round
+__device__ __forceinline__ void
+grb3_block_append(bool take, uint32_t item, uint32_t item2, uint32_t* list, uint32_t* list2,
+                  uint32_t* counter, uint32_t* s_n, uint32_t* s_base)
 {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned m = __ballot_sync(0xffffffffu, take);
+  uint32_t wbase = 0;
+  if (lane == 0 && m) {
+    wbase = atomicAdd(s_n, (uint32_t)__popc(m));
+  }
+  wbase = __shfl_sync(0xffffffffu, wbase, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t n = *s_n;
+    *s_base = n ? atomicAdd(counter, n) : 0u;
+    *s_n = 0;
+  }
+  __syncthreads();
+  if (take) {
+    const uint32_t at = *s_base + wbase + __popc(m & ((1u << lane) - 1u));
+    list[at] = item;
+    if (list2) {
+      list2[at] = item2;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t
+grb3_set_mask(uint32_t n_cand, uint32_t cap_mask)
+{
+  uint32_t want = 1024;
+  while (want < 2u * n_cand && want - 1 < cap_mask) {
+    want <<= 1;
+  }
+  return (want - 1) & cap_mask;
+}
+
+__global__ void __launch_bounds__(256)
+k3_mark(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
+        const GrbSelState* __restrict__ state)
+{
+  __shared__ uint32_t s_n, s_base;
   if (state->halt) {
     return;
   }
+  if (threadIdx.x == 0) {
+    s_n = 0;
+  }
+  __syncthreads();
   const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
   const uint32_t per_tile = T * h;
   for (uint32_t bt = blockIdx.x; bt < bd.n_bt; bt += gridDim.x) {
     const uint32_t b = bd.tile_read[bt];
     const uint32_t t = bt - bd.tile_first[b];
     const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, k);
-    for (uint32_t rem = threadIdx.x; rem < per_tile; rem += blockDim.x) {
-      const uint32_t f = rem / h, p = rem - f * h;
-      if (tl < k + p || f >= tl - (k + p) + 1) {
-        continue;
-      }
+    for (uint32_t base = 0; base < per_tile; base += blockDim.x) {
+      const uint32_t rem = base + threadIdx.x;
+      bool take = false;
       const uint32_t idx = bt * per_tile + rem;
-      const uint64_t rank = __ldcs(&bd.stash[idx]) & ~GRB_STASH_NOFRAME;
-      const uint64_t mine = grb_ix_pack(rank, idx);
-      uint64_t slot = grb_mix64(rank) & b3.ix_mask;
-      while (true) {
-        const unsigned long long old = atomicCAS(&b3.ix_tab[slot], GRB_IX_EMPTY, mine);
-        if (old == GRB_IX_EMPTY) {
-          break;
+      if (rem < per_tile) {
+        const uint32_t f = rem / h, p = rem - f * h;
+        if (tl >= k + p && f < tl - (k + p) + 1) {
+          const uint64_t rank = __ldcs(&bd.stash[idx]) & ~GRB_STASH_NOFRAME;
+          const uint32_t bit = (uint32_t)(grb_mix64(rank) >> 20) & b3.bm_mask;
+          const uint32_t m = 1u << (bit & 31);
+          take = (atomicOr(&b3.bm[bit >> 5], m) & m) != 0;
         }
-        if ((old >> 27) == rank) {
-          const unsigned long long prev = atomicOr(&b3.ix_tab[slot], GRB_IX_FLAG);
-          if (!(prev & GRB_IX_FLAG)) { // first duplicate: open the shared entry, list the owner
-            const uint32_t sidx = atomicAdd(&b3.counters[1], 1u);
-            b3.ix_sidx[slot] = sidx;
-            const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(&filt.slots[rank]));
-            GrbShared3 e;
-            e.rank = rank;
-            e.id0 = raw.x;
-            e.count0 = raw.y;
-            e.off = 0;
-            e.n = 0;
-            e.id = raw.x;
-            e.count = raw.y;
-            b3.shared[sidx] = e;
-            b3.m_fill[sidx] = 0;
-            const uint32_t ci = atomicAdd(&b3.counters[0], 1u);
-            b3.c_slot[ci] = (uint32_t)slot;
-            b3.c_probe[ci] = (uint32_t)((prev >> 1) & 0x3FFFFFFu);
-          }
-          const uint32_t ci = atomicAdd(&b3.counters[0], 1u);
-          b3.c_slot[ci] = (uint32_t)slot;
-          b3.c_probe[ci] = idx;
-          break;
-        }
-        slot = (slot + 1) & b3.ix_mask;
       }
+      grb3_block_append(take, idx, 0, b3.cand, nullptr, &b3.counters[GRB_CTR_CAND], &s_n, &s_base);
     }
   }
 }
 
-// Per conflict: count it for its shared rank, mark its stash entries (stale-tail repeats
-// included) with its conflict index, and list the frames it votes in, once each.
+// clears the part of the exact set this batch will use (its size follows the candidate count)
+__global__ void __launch_bounds__(256)
+k3_set_clear(GrbB3 b3, const GrbSelState* __restrict__ state)
+{
+  if (state->halt) {
+    return;
+  }
+  const uint32_t mask = grb3_set_mask(b3.counters[GRB_CTR_CAND], (uint32_t)b3.ix_mask);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= mask; i += gridDim.x * blockDim.x) {
+    b3.ix_tab[i] = GRB_IX_EMPTY;
+    b3.ix_cnt[i] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k3_dupset(GrbBatchDev bd, GrbB3 b3, const GrbSelState* __restrict__ state)
+{
+  if (state->halt) {
+    return;
+  }
+  const uint32_t n_cand = b3.counters[GRB_CTR_CAND];
+  const uint32_t mask = grb3_set_mask(n_cand, (uint32_t)b3.ix_mask);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_cand; i += gridDim.x * blockDim.x) {
+    const uint64_t rank = bd.stash[b3.cand[i]] & ~GRB_STASH_NOFRAME;
+    uint32_t slot = (uint32_t)grb_mix64(rank) & mask;
+    while (true) {
+      const unsigned long long old = atomicCAS(&b3.ix_tab[slot], GRB_IX_EMPTY, rank);
+      if (old == GRB_IX_EMPTY || old == rank) {
+        break;
+      }
+      slot = (slot + 1) & mask;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k3_members(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
+           const GrbSelState* __restrict__ state)
+{
+  __shared__ uint32_t s_n, s_base;
+  if (state->halt) {
+    return;
+  }
+  if (threadIdx.x == 0) {
+    s_n = 0;
+  }
+  __syncthreads();
+  const uint32_t n_cand = b3.counters[GRB_CTR_CAND];
+  if (n_cand == 0) {
+    return;
+  }
+  const uint32_t mask = grb3_set_mask(n_cand, (uint32_t)b3.ix_mask);
+  const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
+  const uint32_t per_tile = T * h;
+  for (uint32_t bt = blockIdx.x; bt < bd.n_bt; bt += gridDim.x) {
+    const uint32_t b = bd.tile_read[bt];
+    const uint32_t t = bt - bd.tile_first[b];
+    const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, k);
+    for (uint32_t base = 0; base < per_tile; base += blockDim.x) {
+      const uint32_t rem = base + threadIdx.x;
+      bool take = false;
+      uint32_t slot = 0;
+      const uint32_t idx = bt * per_tile + rem;
+      if (rem < per_tile) {
+        const uint32_t f = rem / h, p = rem - f * h;
+        if (tl >= k + p && f < tl - (k + p) + 1) {
+          const uint64_t rank = __ldcs(&bd.stash[idx]) & ~GRB_STASH_NOFRAME;
+          slot = (uint32_t)grb_mix64(rank) & mask;
+          while (true) {
+            const unsigned long long key = __ldcg(&b3.ix_tab[slot]);
+            if (key == rank) {
+              take = true;
+              break;
+            }
+            if (key == GRB_IX_EMPTY) {
+              break;
+            }
+            slot = (slot + 1) & mask;
+          }
+          if (take) {
+            atomicAdd(&b3.ix_cnt[slot], 1u);
+          }
+        }
+      }
+      grb3_block_append(take, idx, slot, b3.t_probe, b3.t_slot, &b3.counters[GRB_CTR_LISTED], &s_n,
+                        &s_base);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k3_open(GrbFilterDev filt, GrbB3 b3, const GrbSelState* __restrict__ state)
+{
+  if (state->halt) {
+    return;
+  }
+  const uint32_t n_cand = b3.counters[GRB_CTR_CAND];
+  if (n_cand == 0) {
+    return;
+  }
+  const uint32_t mask = grb3_set_mask(n_cand, (uint32_t)b3.ix_mask);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= mask; i += gridDim.x * blockDim.x) {
+    const uint32_t n = b3.ix_cnt[i];
+    if (n < 2) {
+      continue;
+    }
+    const uint64_t rank = b3.ix_tab[i];
+    const uint32_t sidx = atomicAdd(&b3.counters[GRB_CTR_SHARED], 1u);
+    b3.ix_sidx[i] = sidx;
+    const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(&filt.slots[rank]));
+    GrbShared3 e;
+    e.rank = rank;
+    e.id0 = raw.x;
+    e.count0 = raw.y;
+    e.off = 0;
+    e.n = n;
+    e.id = raw.x;
+    e.count = raw.y;
+    b3.shared[sidx] = e;
+    b3.m_fill[sidx] = 0;
+  }
+}
+
+// Per listed probe of a shared rank: it becomes a conflict; mark its stash entries (stale-tail
+// repeats included) with its conflict index, and list the frames it votes in, once each.
 __global__ void __launch_bounds__(256)
 k3_conf(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
         const GrbSelState* __restrict__ state)
@@ -150,12 +312,17 @@ k3_conf(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
     return;
   }
   const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
-  const uint32_t n_conf = b3.counters[0];
-  for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n_conf; ci += gridDim.x * blockDim.x) {
-    const uint32_t sidx = b3.ix_sidx[b3.c_slot[ci]];
-    const uint32_t probe = b3.c_probe[ci];
+  const uint32_t n_listed = b3.counters[GRB_CTR_LISTED];
+  for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_listed; li += gridDim.x * blockDim.x) {
+    const uint32_t slot = b3.t_slot[li];
+    if (b3.ix_cnt[slot] < 2) {
+      continue; // false positive of the bit map: the rank is private
+    }
+    const uint32_t sidx = b3.ix_sidx[slot];
+    const uint32_t probe = b3.t_probe[li];
+    const uint32_t ci = atomicAdd(&b3.counters[GRB_CTR_CONF], 1u);
+    b3.c_probe[ci] = probe;
     b3.c_sidx[ci] = sidx;
-    atomicAdd(&b3.shared[sidx].n, 1u);
     const GrbProbeAt a = grb2_probe_at(reads, prm, bd, probe);
     const uint32_t frames = a.tl - k + 1;
     const uint32_t n_p = a.tl - (k + a.p) + 1;

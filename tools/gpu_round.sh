@@ -18,7 +18,7 @@ if [[ " $* " == *" ncu "* ]]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file $OUT/launches_$TAG.csv python bench.py --steps 1 --warmup 1 > $OUT/ncu_bench_$TAG.log 2>&1
   echo "ncu launches exit $?"
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_spec_query -s 40 -c 1 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-k2_query} -s ${NCU_SKIP:-40} -c 1 \
     -o $OUT/ncu_query_$TAG -f python bench.py --steps 1 --warmup 1 > $OUT/ncu_full_$TAG.log 2>&1
   echo "ncu full exit $?"
 fi

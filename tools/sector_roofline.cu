@@ -79,6 +79,24 @@ k_rmw(ulonglong2* __restrict__ mem, uint64_t n_slots, uint64_t per_thread, uint6
   }
 }
 
+// random 64-bit atomicOr (the pass-1 bit fill) / atomicCAS (the batch rank index)
+__global__ void
+k_atom(unsigned long long* __restrict__ mem, uint64_t n_words, uint64_t per_thread, uint64_t seed,
+       int cas)
+{
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t x = splitmix(seed ^ tid);
+  for (uint64_t i = 0; i < per_thread; ++i) {
+    x = splitmix(x);
+    const uint64_t s = (uint64_t)(((unsigned __int128)x * n_words) >> 64);
+    if (cas) {
+      atomicCAS(mem + s, 0x0101010101010101ull, x);
+    } else {
+      atomicOr(mem + s, 1ull << (x & 63));
+    }
+  }
+}
+
 int
 main(int argc, char** argv)
 {
@@ -120,14 +138,16 @@ main(int argc, char** argv)
       const uint64_t threads = (uint64_t)sms * 2048;
       const uint64_t per_thread = 256;
       const unsigned grid = (unsigned)(threads / 256);
-      for (int mode = 0; mode < 2; ++mode) {
+      for (int mode = 0; mode < 4; ++mode) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; ++rep) {
           CK(cudaEventRecord(e0));
           if (mode == 0) {
             k_gather<<<grid, 256>>>((const ulonglong2*)mem, bytes / 32, per_thread, 42 + rep, sink);
-          } else {
+          } else if (mode == 1) {
             k_rmw<<<grid, 256>>>((ulonglong2*)mem, bytes / 16, per_thread, 42 + rep);
+          } else {
+            k_atom<<<grid, 256>>>((unsigned long long*)mem, bytes / 8, per_thread, 42 + rep, mode == 3);
           }
           CK(cudaEventRecord(e1));
           CK(cudaEventSynchronize(e1));
@@ -141,7 +161,7 @@ main(int argc, char** argv)
         const double gbs = acc * (mode == 0 ? 32.0 : 64.0) / (best * 1e-3) / 1e9;
         printf("%s{\"granularity_limit\": %zu, \"footprint_gib\": %.4f, \"op\": \"%s\", "
                "\"accesses\": %.0f, \"ms\": %.4f, \"gacc_per_s\": %.3f, \"sector_gb_per_s\": %.1f}",
-               first ? "" : ",\n", got, g, mode == 0 ? "gather32" : "rmw16", acc, best,
+               first ? "" : ",\n", got, g, mode == 0 ? "gather32" : (mode == 1 ? "rmw16" : (mode == 2 ? "atomic_or64" : "atomic_cas64")), acc, best,
                acc / (best * 1e-3) / 1e9, gbs);
         first = false;
       }
