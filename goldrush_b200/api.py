@@ -122,6 +122,9 @@ def lib():
         "grb_destroy": (None, [vp]),
         "grb_last_error": (C.c_char_p, [vp]),
         "grb_launch_count": (u64, [vp]),
+        "grb_cached_memory_bytes": (u64, []),
+        "grb_release_cached_memory": (None, []),
+        "grb_reads_reserve": (i32, [vp, u64]),
         "grb_reads_ingest_fastq": (i32, [vp, vp, sz, i32, P(sz)]),
         "grb_reads_count": (u64, [vp]),
         "grb_reads_get_meta": (i32, [vp, u64, u64, P(ReadMeta)]),

@@ -107,6 +107,13 @@ struct grb_ctx;
     }                                                                                              \
   } while (0)
 
+// Process-wide cache of device allocations (engine.cu).  cudaMalloc / cudaFree of the tens of GB behind
+// a filter cost hundreds of milliseconds each, so a destroyed context hands its blocks back to the
+// cache and the next context of the same shape (the next grb_run_path call of a service, the next
+// bench step) takes them over.  grb_release_cached_memory() empties it; GRB_POOL=0 turns it off.
+cudaError_t grb_pool_alloc(void** p, size_t bytes);
+void grb_pool_free(void* p);
+
 template<typename T>
 struct DevBuf
 {
@@ -116,7 +123,7 @@ struct DevBuf
   void release()
   {
     if (p) {
-      cudaFree(p);
+      grb_pool_free(p);
     }
     p = nullptr;
     cap = 0;
@@ -129,10 +136,10 @@ struct DevBuf
     }
     size_t ncap = n + n / 2 + 64;
     T* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, ncap * sizeof(T));
+    cudaError_t e = grb_pool_alloc((void**)&q, ncap * sizeof(T));
     if (e != cudaSuccess) {
       ncap = n;
-      e = cudaMalloc(&q, ncap * sizeof(T));
+      e = grb_pool_alloc((void**)&q, ncap * sizeof(T));
       if (e != cudaSuccess) {
         return e;
       }
@@ -140,16 +147,35 @@ struct DevBuf
     if (p && keep) {
       e = cudaMemcpyAsync(q, p, keep * sizeof(T), cudaMemcpyDeviceToDevice, s);
       if (e != cudaSuccess) {
-        cudaFree(q);
+        grb_pool_free(q);
         return e;
       }
-      cudaStreamSynchronize(s);
     }
     if (p) {
-      cudaFree(p);
+      // the old block may be handed to another context: nothing of this stream may still use it
+      cudaStreamSynchronize(s);
+      grb_pool_free(p);
     }
     p = q;
     cap = ncap;
     return cudaSuccess;
+  }
+  // exact-size variant for the big one-shot buffers (no 1.5x slack)
+  cudaError_t reserve_exact(size_t n, cudaStream_t s)
+  {
+    if (n <= cap) {
+      return cudaSuccess;
+    }
+    if (p) {
+      cudaStreamSynchronize(s);
+      grb_pool_free(p);
+      p = nullptr;
+      cap = 0;
+    }
+    cudaError_t e = grb_pool_alloc((void**)&p, n * sizeof(T));
+    if (e == cudaSuccess) {
+      cap = n;
+    }
+    return e;
   }
 };

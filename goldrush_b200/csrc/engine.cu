@@ -20,6 +20,126 @@ const uint64_t kSeedBase[4] = { 0x3c8bfbb395c60474ULL, 0x3193c18562a02b4cULL,
                                 0x20323ed082572324ULL, 0x295549f54be24456ULL };
 }
 
+
+// ---- process-wide device allocation cache (declared in common.cuh) ---------------------------
+#include <map>
+#include <mutex>
+#include <unordered_map>
+namespace {
+struct GrbPool
+{
+  std::mutex mu;
+  struct Block
+  {
+    size_t bytes;
+    int device;
+  };
+  std::unordered_map<void*, Block> live;                     // handed out
+  std::multimap<std::pair<int, size_t>, void*> idle;         // (device, bytes) -> block
+  size_t idle_bytes = 0;
+  bool enabled = true;
+  GrbPool()
+  {
+    if (const char* e = getenv("GRB_POOL")) {
+      enabled = strcmp(e, "0") != 0;
+    }
+  }
+  static size_t round_up(size_t b)
+  {
+    const size_t g = b >= (1u << 20) ? (2u << 20) : 512; // 2 MiB pages for anything big
+    return (std::max<size_t>(b, 1) + g - 1) / g * g;
+  }
+  void trim_locked(int device)
+  {
+    for (auto it = idle.begin(); it != idle.end();) {
+      if (device < 0 || it->first.first == device) {
+        cudaFree(it->second);
+        idle_bytes -= it->first.second;
+        it = idle.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+};
+GrbPool&
+pool()
+{
+  static GrbPool* p = new GrbPool; // leaked on purpose: no CUDA calls during static destruction
+  return *p;
+}
+} // namespace
+
+cudaError_t
+grb_pool_alloc(void** out, size_t bytes)
+{
+  GrbPool& P = pool();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t need = GrbPool::round_up(bytes);
+  std::lock_guard<std::mutex> lk(P.mu);
+  if (P.enabled) {
+    // smallest idle block that fits without wasting more than a quarter of it
+    auto it = P.idle.lower_bound({ dev, need });
+    if (it != P.idle.end() && it->first.first == dev && it->first.second <= need + need / 4 + (2u << 20)) {
+      *out = it->second;
+      P.live[*out] = GrbPool::Block{ it->first.second, dev };
+      P.idle_bytes -= it->first.second;
+      P.idle.erase(it);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(out, need);
+  if (e != cudaSuccess && P.idle_bytes) {
+    cudaGetLastError();
+    P.trim_locked(dev); // give the cache back to the driver and try once more
+    e = cudaMalloc(out, need);
+  }
+  if (e == cudaSuccess) {
+    P.live[*out] = GrbPool::Block{ need, dev };
+  }
+  return e;
+}
+
+void
+grb_pool_free(void* p)
+{
+  if (!p) {
+    return;
+  }
+  GrbPool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  auto it = P.live.find(p);
+  if (it == P.live.end()) {
+    cudaFree(p);
+    return;
+  }
+  const GrbPool::Block b = it->second;
+  P.live.erase(it);
+  if (P.enabled) {
+    P.idle.insert({ { b.device, b.bytes }, p });
+    P.idle_bytes += b.bytes;
+  } else {
+    cudaFree(p);
+  }
+}
+
+extern "C" void
+grb_release_cached_memory(void)
+{
+  GrbPool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  P.trim_locked(-1);
+}
+
+extern "C" uint64_t
+grb_cached_memory_bytes(void)
+{
+  GrbPool& P = pool();
+  std::lock_guard<std::mutex> lk(P.mu);
+  return P.idle_bytes;
+}
+
 struct grb_ctx
 {
   grb_params p{};
@@ -383,7 +503,7 @@ grb_create(const grb_params* p, grb_ctx** out)
       c->batch_reads = (uint32_t)v;
     }
   }
-  if ((e = cudaMalloc(&c->d_seed, sizeof(GrbSeedTables))) != cudaSuccess ||
+  if ((e = grb_pool_alloc((void**)&c->d_seed, sizeof(GrbSeedTables))) != cudaSuccess ||
       (e = cudaMemcpy(c->d_seed, &c->h_seed, sizeof(GrbSeedTables), cudaMemcpyHostToDevice)) !=
         cudaSuccess) {
     return bail(GRB_ERR_CUDA, std::string("seed table upload: ") + cudaGetErrorString(e));
@@ -412,18 +532,10 @@ grb_destroy(grb_ctx* c)
   if (c->stream) {
     cudaStreamSynchronize(c->stream);
   }
-  if (c->filt.blocks) {
-    cudaFree(c->filt.blocks);
-  }
-  if (c->filt.slots) {
-    cudaFree(c->filt.slots);
-  }
-  if (c->d_state) {
-    cudaFree(c->d_state);
-  }
-  if (c->d_seed) {
-    cudaFree(c->d_seed);
-  }
+  grb_pool_free(c->filt.blocks);
+  grb_pool_free(c->filt.slots);
+  grb_pool_free(c->d_state);
+  grb_pool_free(c->d_seed);
   if (c->ev0) {
     cudaEventDestroy(c->ev0);
   }
@@ -503,6 +615,21 @@ grb_reads_clear(grb_ctx* c)
   c->h_word_off.clear();
   c->h_flags.clear();
   c->h_meta.clear();
+}
+
+int
+grb_reads_reserve(grb_ctx* c, uint64_t fastq_bytes)
+{
+  cudaSetDevice(c->device);
+  if (c->n_reads != 0) {
+    return GRB_OK; // only a hint, and only before the first record
+  }
+  // a record is at least 2 * len + 6 bytes, so bases <= fastq_bytes / 2; +1 word per read for the
+  // word alignment of every read (reads of 64 bases or more: <= bases / 64 extra words)
+  const uint64_t words = fastq_bytes / 64 + fastq_bytes / 128 + 64;
+  GRB_CUDA(c, c->d_bases.reserve_exact(c->n_words + words + 4, c->stream));
+  GRB_CUDA(c, c->d_nmask.reserve_exact(c->n_words + words + 4, c->stream));
+  return GRB_OK;
 }
 
 int
@@ -744,11 +871,12 @@ grb_filter_alloc(grb_ctx* c, uint64_t filter_bits)
   // cost more than the rank build)
   if (c->filt.n_blocks * 32 > c->blocks_cap) {
     if (c->filt.blocks) {
-      cudaFree(c->filt.blocks);
+      cudaStreamSynchronize(c->stream);
+      grb_pool_free(c->filt.blocks);
       c->filt.blocks = nullptr;
       c->blocks_cap = 0;
     }
-    GRB_CUDA(c, cudaMalloc(&c->filt.blocks, c->filt.n_blocks * 32));
+    GRB_CUDA(c, grb_pool_alloc((void**)&c->filt.blocks, c->filt.n_blocks * 32));
     c->blocks_cap = c->filt.n_blocks * 32;
   }
   GRB_CUDA(c, cudaMemsetAsync(c->filt.blocks, 0, c->filt.n_blocks * 32, c->stream));
@@ -840,11 +968,12 @@ grb_finalize_bitvector(grb_ctx* c, uint64_t* pop)
   // m_data + m_counts (MIBloomFilter.hpp:165-184, MIBFConstructSupport.hpp:175-181), zeroed
   if ((total + 1) * sizeof(GrbSlot) > c->slots_cap) {
     if (c->filt.slots) {
-      cudaFree(c->filt.slots);
+      cudaStreamSynchronize(s);
+      grb_pool_free(c->filt.slots);
       c->filt.slots = nullptr;
       c->slots_cap = 0;
     }
-    GRB_CUDA(c, cudaMalloc(&c->filt.slots, (total + 1) * sizeof(GrbSlot)));
+    GRB_CUDA(c, grb_pool_alloc((void**)&c->filt.slots, (total + 1) * sizeof(GrbSlot)));
     c->slots_cap = (total + 1) * sizeof(GrbSlot);
   }
   GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, (total + 1) * sizeof(GrbSlot), s));
@@ -1080,7 +1209,7 @@ sel_prepare(grb_ctx* c, uint64_t max_len)
     GRB_CUDA(c, cudaFuncSetAttribute(k_query<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)c->query_smem));
     if (!c->d_state) {
-      GRB_CUDA(c, cudaMalloc(&c->d_state, sizeof(GrbSelState)));
+      GRB_CUDA(c, grb_pool_alloc((void**)&c->d_state, sizeof(GrbSelState)));
     }
     GrbSelState st{};
     st.curr_path = 1;

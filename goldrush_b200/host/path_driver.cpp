@@ -223,6 +223,9 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
     return set_err(err, err_cap, "Gold Path requires fastq format", GRB_ERR_FORMAT);
   }
   {
+    if ((rc = grb_reads_reserve(ctx, n)) != GRB_OK) {
+      return fail(rc);
+    }
     const size_t kChunk = (size_t)1 << 30;
     size_t off = 0;
     while (off < n) {

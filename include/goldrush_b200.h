@@ -80,6 +80,15 @@ void grb_destroy(grb_ctx* ctx);
 const char* grb_last_error(const grb_ctx* ctx); /* ctx may be NULL: message of a failed grb_create */
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 uint64_t grb_launch_count(const grb_ctx* ctx);
+/* Device allocations of a destroyed context are kept in a process-wide cache and handed to the next
+ * context of the same shape (the reference re-allocates its filter per process,
+ * MIBFConstructSupport.hpp:66-84 — a resident service or the bench loop need not).  These two
+ * calls report and empty that cache; GRB_POOL=0 in the environment disables it. */
+uint64_t grb_cached_memory_bytes(void);
+void grb_release_cached_memory(void);
+/* Size hint before the first grb_reads_ingest_fastq: total FASTQ bytes to come, so that the read
+ * store is allocated once instead of grown chunk by chunk. */
+int grb_reads_reserve(grb_ctx* ctx, uint64_t fastq_bytes);
 
 /* ---- K1: FASTQ decode + Phred sums into the device read store ----
  * replaces btllib::SeqReader (goldrush_path.cpp:87,246; read_hashing.cpp:89-90; ntcard.hpp:200)
