@@ -235,6 +235,9 @@ def bench_ours(args, w):
     cudart = torch.cuda.cudart()
     pinned = int(cudart.cudaHostRegister(fq_ptr, fq_len, 0)) == 0
 
+    if world > 1:
+        from goldrush_b200 import multi
+        multi.init_comm(local)
     seeds = grb.make_seed_pattern(SEED22, PARAMS["kmer_size"], PARAMS["weight"], PARAMS["hash_num"])
     eng = grb.Engine(seeds, device=local, genome_size=w["genome"],
                      **{k: v for k, v in PARAMS.items() if k not in ("kmer_size", "hash_num")})
@@ -255,26 +258,12 @@ def bench_ours(args, w):
     filter_bits = grb.calc_optimal_size(hash_universe, 1, PARAMS["occupancy"])
     bases_pass1 = int(meta["len"][flags & 1 != 0].sum())
 
-    # multi-GPU: pass 1 is sharded over reads and OR-reduced (all-gather + OR kernel); the ordered
-    # selection loop is replicated on every rank (multi-GPU)
-    lo, hi = rank * n_reads // world, (rank + 1) * n_reads // world
-
+    # multi-GPU: the engine was created after multi.init_comm, so the library itself
+    # shards pass 1 (+ OR-reduce) and each batch's speculative query (+ all-gather) over NCCL; the
+    # ordered commit is replicated.  Same call sequence at every N.
     def one_step():
         eng.filter_alloc(filter_bits)
-        if world == 1:
-            eng.build_bitvector()
-        else:
-            eng.build_bitvector(lo, hi - lo)
-            ptr, nbytes = eng.bitvector_device()
-            mine = _as_tensor(torch, ptr, nbytes, local)
-            with torch.cuda.stream(stream):
-                gathered = torch.empty((world, nbytes // 8), dtype=torch.int64, device=mine.device)
-                dist.all_gather_into_tensor(gathered, mine)
-            for r in range(world):
-                if r != rank:
-                    eng.or_words(ptr, gathered[r].data_ptr(), nbytes // 8)
-            eng.sync()
-            del gathered
+        eng.build_bitvector()
         pop = eng.finalize_bitvector()
         dec, stats, fin = eng.select_reads_array()
         return pop, dec
@@ -311,6 +300,8 @@ def bench_ours(args, w):
     commit_prof = eng.commit_profile()
     eng.profile_enable(False)
 
+    if world > 1:  # the commit is replicated: every rank must hold the same decisions
+        multi.assert_replicas_agree(dec.view(np.uint8))
     visited = dec["verdict"] >= 2
     bases_pass2 = int((dec["num_tiles"][visited].astype(np.int64) * PARAMS["tile_length"]).sum())
     reads_visited = int(visited.sum())
@@ -414,6 +405,10 @@ def bench_ours(args, w):
                        "reads_selected": int(selected.sum()), "bases_pass1": bases_pass1,
                        "bases_pass2": bases_pass2, "filter_bits": int(filter_bits), "pop": int(pop),
                        "l2": "inputs larger than L2 (filter blocks + ID slots + packed reads)",
+                       "parallelism": ("one GPU" if world == 1 else
+                                       f"filter replicated on {world} GPUs; pass-1 reads and each "
+                                       f"batch's query tiles sharded, NCCL OR-reduce / all-gather; "
+                                       f"ordered commit replicated (decisions checked equal)"),
                        "synth_s": round(t_synth, 1)},
             "kernels_ms_per_step": {k: v[0] / args.steps for k, v in ktime.items()},
             "commit_profile_last_step": commit_prof,
@@ -422,17 +417,8 @@ def bench_ours(args, w):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
+        grb.api.comm_destroy()
         dist.destroy_process_group()
-
-
-class _DevMem:
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8",
-                                         "data": (ptr, False), "version": 2}
-
-
-def _as_tensor(torch, ptr, nbytes, device):
-    return torch.as_tensor(_DevMem(ptr, nbytes), device=torch.device("cuda", device))
 
 
 def main():

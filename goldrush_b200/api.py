@@ -96,7 +96,7 @@ DECISION_DTYPE = np.dtype([("verdict", "u1"), ("pad", "u1", (3,)), ("path", "<u4
 
 VERDICTS = {0: "not_visited", 1: "skipped", 2: "untrimmed", 3: "trimmed", 4: "assigned"}
 READ_PASS1, READ_PASS2 = 1, 2
-KERNEL_CLASSES = ["fill", "rank", "query", "decide", "insert", "smooth", "dedupe", "commit"]
+KERNEL_CLASSES = ["fill", "rank", "query", "decide", "insert", "smooth", "dedupe", "commit", "gather"]
 
 _lib = None
 
@@ -147,6 +147,10 @@ def lib():
         "grb_set_ids": (i32, [vp, vp, sz, vp, vp]),
         "grb_query_read": (i32, [vp, u64, vp, vp, vp, vp, vp, u32, vp]),
         "grb_insert_tiles": (i32, [vp, u64, u32, u32, u32]),
+        "grb_comm_unique_id": (i32, [vp]),
+        "grb_comm_init": (i32, [vp, i32, i32, i32]),
+        "grb_comm_destroy": (None, []),
+        "grb_comm_info": (i32, [vp, P(i32), P(i32)]),
         "grb_bitvector_device": (i32, [vp, P(vp), P(u64)]),
         "grb_or_words": (i32, [vp, vp, vp, u64]),
         "grb_sync": (i32, [vp]),
@@ -194,6 +198,37 @@ def phred_finalize(first_half_sum, total_sum, n):
     a, d = C.c_uint32(), C.c_uint32()
     lib().grb_phred_finalize(first_half_sum, total_sum, n, C.byref(a), C.byref(d))
     return a.value, d.value
+
+
+# ---- multi-GPU: the process-wide NCCL communicator of the library (include/goldrush_b200.h) ------
+def comm_unique_id() -> bytes:
+    """Rank 0: a fresh NCCL unique id (128 bytes) to hand to every other rank."""
+    buf = C.create_string_buffer(128)
+    rc = lib().grb_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc:
+        raise GrbError(rc, (lib().grb_last_error(None) or b"").decode())
+    return buf.raw
+
+
+def comm_init(ident: bytes, rank: int, world: int, device: int):
+    """Every rank: joins the communicator; Engines / run_path created afterwards on `device` shard
+    pass 1 and the speculative query across the ranks."""
+    if len(ident) != 128:
+        raise GrbError(-1, "comm_init: the NCCL unique id is 128 bytes")
+    buf = C.create_string_buffer(ident, 128)
+    rc = lib().grb_comm_init(C.cast(buf, C.c_void_p), rank, world, device)
+    if rc:
+        raise GrbError(rc, (lib().grb_last_error(None) or b"").decode())
+
+
+def comm_destroy():
+    lib().grb_comm_destroy()
+
+
+def comm_info(engine=None):
+    r, w = C.c_int(), C.c_int()
+    lib().grb_comm_info(engine._h if engine is not None else None, C.byref(r), C.byref(w))
+    return r.value, w.value
 
 
 def default_params(**kw):

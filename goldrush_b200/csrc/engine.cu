@@ -8,6 +8,7 @@
 #include "kernels_batch.cuh"
 #include "kernels_batch2.cuh"
 #include "kernels_fix.cuh"
+#include "comm.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -185,6 +186,8 @@ struct grb_ctx
   uint64_t blocks_cap = 0, slots_cap = 0; // bytes allocated behind filt.blocks / filt.slots
   DevBuf<uint32_t> d_chunk_read;
   DevBuf<uint64_t> d_chunk_first;
+  DevBuf<uint32_t> fill_lists, fill_cursor; // partitioned fill (kernels_filter.cuh)
+  bool fill_attr = false;
 
   // ---- selection loop ----
   GrbSelParams prm{};
@@ -247,6 +250,16 @@ struct grb_ctx
   DevBuf<GrbReadPlan> b3_np;
   DevBuf<GrbFixCtl> b3_ctl;
   DevBuf<unsigned long long> b3_d_keys, b3_barrier;
+
+  // ---- multi-GPU (comm.cuh): the process-wide NCCL communicator, when this context's device is
+  // the one it was created on and it spans more than one rank ----
+  GrbComm* comm = nullptr;
+  DevBuf<uint64_t> comm_tmp; // all-gather landing zone of the pass-1 OR-reduce
+  int fail_nccl(ncclResult_t r, const char* what)
+  {
+    err = std::string(what) + ": " + comm->api.GetErrorString(r);
+    return GRB_ERR_CUDA;
+  }
 
   // ---- per-kernel-class device timing (grb_profile_enable / grb_kernel_time) ----
   bool prof_on = false;
@@ -503,6 +516,14 @@ grb_create(const grb_params* p, grb_ctx** out)
       c->batch_reads = (uint32_t)v;
     }
   }
+  {
+    GrbComm& g = grb_comm();
+    std::lock_guard<std::mutex> lk(g.mu);
+    const char* off = getenv("GRB_COMM");
+    if (g.comm && g.world > 1 && g.device == c->device && !(off && strcmp(off, "0") == 0)) {
+      c->comm = &g;
+    }
+  }
   if ((e = grb_pool_alloc((void**)&c->d_seed, sizeof(GrbSeedTables))) != cudaSuccess ||
       (e = cudaMemcpy(c->d_seed, &c->h_seed, sizeof(GrbSeedTables), cudaMemcpyHostToDevice)) !=
         cudaSuccess) {
@@ -565,6 +586,93 @@ int
 grb_stream(grb_ctx* c, void** cuda_stream)
 {
   *cuda_stream = (void*)c->stream;
+  return GRB_OK;
+}
+
+// ---- multi-GPU: process-wide communicator (one process per GPU) ----
+int
+grb_comm_unique_id(uint8_t* out128)
+{
+  GrbComm& g = grb_comm();
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (!grb_nccl_load(g)) {
+    g_create_error = g.err;
+    return GRB_ERR_STATE;
+  }
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes in the ABI this binds");
+  ncclUniqueId id;
+  const ncclResult_t r = g.api.GetUniqueId(&id);
+  if (r != ncclSuccess) {
+    g_create_error = g.err = std::string("ncclGetUniqueId: ") + g.api.GetErrorString(r);
+    return GRB_ERR_CUDA;
+  }
+  memcpy(out128, &id, 128);
+  return GRB_OK;
+}
+
+int
+grb_comm_init(const uint8_t* id128, int rank, int world, int device)
+{
+  GrbComm& g = grb_comm();
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (world < 1 || rank < 0 || rank >= world || !id128) {
+    g_create_error = g.err = "grb_comm_init: rank / world out of range";
+    return GRB_ERR_ARG;
+  }
+  if (g.comm) {
+    g_create_error = g.err = "grb_comm_init: a communicator already exists (grb_comm_destroy first)";
+    return GRB_ERR_STATE;
+  }
+  if (!grb_nccl_load(g)) {
+    g_create_error = g.err;
+    return GRB_ERR_STATE;
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    g_create_error = g.err = std::string("grb_comm_init: ") + cudaGetErrorString(e);
+    return GRB_ERR_CUDA;
+  }
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  const ncclResult_t r = g.api.CommInitRank(&g.comm, world, id, rank);
+  if (r != ncclSuccess) {
+    g.comm = nullptr;
+    g_create_error = g.err = std::string("ncclCommInitRank: ") + g.api.GetErrorString(r);
+    return GRB_ERR_CUDA;
+  }
+  g.rank = rank;
+  g.world = world;
+  g.device = device;
+  return GRB_OK;
+}
+
+void
+grb_comm_destroy(void)
+{
+  GrbComm& g = grb_comm();
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.comm) {
+    g.api.CommDestroy(g.comm);
+  }
+  g.comm = nullptr;
+  g.rank = 0;
+  g.world = 1;
+  g.device = -1;
+}
+
+int
+grb_comm_info(const grb_ctx* c, int* rank, int* world)
+{
+  // c == NULL: the process-wide communicator; else what this context actually uses
+  if (c) {
+    *rank = c->comm ? c->comm->rank : 0;
+    *world = c->comm ? c->comm->world : 1;
+  } else {
+    GrbComm& g = grb_comm();
+    std::lock_guard<std::mutex> lk(g.mu);
+    *rank = g.rank;
+    *world = g.world;
+  }
   return GRB_OK;
 }
 
@@ -924,12 +1032,119 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
     GRB_CUDA(c, cudaMemcpyAsync(c->d_chunk_first.p, chunk_first.data(), c->n_reads * 8,
                                 cudaMemcpyHostToDevice, s));
     c->tic();
-    c->kbegin();
-    k_fill_bits<<<grid_for(chunk_read.size(), 1, c->sm_count * 16), 256, 0, s>>>(
-      c->reads_dev(), c->d_seed, c->filt, c->d_chunk_read.p, c->d_chunk_first.p, chunk_read.size());
-    c->kend(GRB_K_FILL);
+    // Partitioned fill (kernels_filter.cuh): worth it once the vector outgrows L2; the direct
+    // kernel stays for small filters, for h > 4 and for A/B runs (GRB_FILL=direct|part).
+    const uint64_t h = c->h_seed.h;
+    uint32_t pshift = 27;
+    if (const char* e = getenv("GRB_FILL_PSHIFT")) { // tests: many partitions on a small filter
+      const long v = strtol(e, nullptr, 10);
+      if (v >= 10 && v <= 31) {
+        pshift = (uint32_t)v;
+      }
+    }
+    while (((c->filt.bits + (1ull << pshift) - 1) >> pshift) > 256) {
+      ++pshift;
+    }
+    const uint32_t n_part = (uint32_t)((c->filt.bits + (1ull << pshift) - 1) >> pshift);
+    const char* mode = getenv("GRB_FILL");
+    bool part = h <= GRB_PART_H && pshift < 32 && n_part >= 2 && c->filt.n_blocks * 32 > (48ull << 20);
+    if (mode && strcmp(mode, "direct") == 0) {
+      part = false;
+    }
+    if (mode && strcmp(mode, "part") == 0) {
+      part = h <= GRB_PART_H && pshift < 32;
+    }
+    if (!part) {
+      c->kbegin();
+      k_fill_bits<<<grid_for(chunk_read.size(), 1, c->sm_count * 16), 256, 0, s>>>(
+        c->reads_dev(), c->d_seed, c->filt, c->d_chunk_read.p, c->d_chunk_first.p, chunk_read.size());
+      c->kend(GRB_K_FILL);
+    } else {
+      // list space: GRB_FILL_SCRATCH_MB (default 2048) split evenly over the partitions; a round
+      // takes as many chunks as fill a full-size partition's list to 1/1.05 of its capacity
+      uint64_t scratch_mb = 2048;
+      if (const char* e = getenv("GRB_FILL_SCRATCH_MB")) {
+        const long v = strtol(e, nullptr, 10);
+        if (v >= 16 && v <= 65536) {
+          scratch_mb = (uint64_t)v;
+        }
+      }
+      const uint64_t max_probes = (uint64_t)chunk_read.size() * GRB_FILL_CHUNK * h;
+      const double share = std::min(1.0, (double)(1ull << pshift) / (double)c->filt.bits);
+      uint64_t cap = std::min<uint64_t>((scratch_mb << 20) / 4 / n_part,
+                                        (uint64_t)((double)max_probes * share * 1.05) + 65536 + 4096);
+      cap = std::min<uint64_t>(std::max<uint64_t>(cap, 131072), 0xFFFFF000u);
+      const uint64_t round_probes =
+        std::max<uint64_t>((uint64_t)((double)(cap - 65536) / 1.05 / share), GRB_FILL_CHUNK * h);
+      const uint64_t round_chunks = std::max<uint64_t>(1, round_probes / (GRB_FILL_CHUNK * h));
+      if (const char* e = getenv("GRB_FILL_CAP")) { // tests: force the list-overflow fallback
+        const long v = strtol(e, nullptr, 10);
+        if (v >= 1 && (uint64_t)v < cap) {
+          cap = (uint64_t)v;
+        }
+      }
+      GRB_CUDA(c, c->fill_lists.reserve(cap * n_part, 0, s));
+      GRB_CUDA(c, c->fill_cursor.reserve(n_part, 0, s));
+      GrbFillPart fp{ c->fill_lists.p, c->fill_cursor.p, n_part, pshift, (uint32_t)cap, 0 };
+      const size_t dyn = ((size_t)GRB_FILL_CHUNK * h + 3 * (size_t)n_part + 1) * 4;
+      const int smem_optin = (int)(((size_t)GRB_FILL_CHUNK * GRB_PART_H + 3 * 512 + 1) * 4);
+      if (!c->fill_attr) {
+        GRB_CUDA(c, cudaFuncSetAttribute(k_fill_part<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_optin));
+        GRB_CUDA(c, cudaFuncSetAttribute(k_fill_part<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         smem_optin));
+        c->fill_attr = true;
+      }
+      // one 1024-thread CTA per SM at 64 registers, or (GRB_FILL_BS=512) one 512-thread CTA at 106
+      const char* bs_env = getenv("GRB_FILL_BS");
+      const bool bs512 = bs_env && strcmp(bs_env, "512") == 0;
+      c->kbegin();
+      uint64_t n_launch = 0;
+      for (uint64_t c0 = 0; c0 < chunk_read.size(); c0 += round_chunks) {
+        const uint64_t nc = std::min<uint64_t>(round_chunks, chunk_read.size() - c0);
+        GRB_CUDA(c, cudaMemsetAsync(fp.cursor, 0, (size_t)n_part * 4, s));
+        if (bs512) {
+          k_fill_part<512><<<grid_for(nc, 1, c->sm_count * 4), 512, dyn, s>>>(
+            c->reads_dev(), c->d_seed, c->filt, c->d_chunk_read.p, c->d_chunk_first.p, c0, nc, fp);
+        } else {
+          k_fill_part<1024><<<grid_for(nc, 1, c->sm_count * 4), 1024, dyn, s>>>(
+            c->reads_dev(), c->d_seed, c->filt, c->d_chunk_read.p, c->d_chunk_first.p, c0, nc, fp);
+        }
+        k_fill_apply<<<c->sm_count * 8, 256, 0, s>>>(c->filt, fp);
+        n_launch += 2;
+      }
+      c->kend(GRB_K_FILL, n_launch);
+    }
   }
   c->toc();
+  GRB_CUDA(c, cudaGetLastError());
+  return GRB_OK;
+}
+
+// Pass 1 on W GPUs: this rank's share of the reads, then the OR-reduce of the W bit vectors
+// (all-gather slice by slice + k_or_gathered; the rank word of every block is still zero here).
+static int
+or_reduce_bitvector(grb_ctx* c)
+{
+  GrbComm& g = *c->comm;
+  cudaStream_t s = c->stream;
+  const uint64_t n_words = c->filt.n_blocks * 4;
+  const uint64_t slice = std::min<uint64_t>(n_words, (64ull << 20) / 8);
+  GRB_CUDA(c, c->comm_tmp.reserve(slice * g.world, 0, s));
+  c->kbegin();
+  uint64_t n_launch = 0;
+  for (uint64_t off = 0; off < n_words; off += slice) {
+    const uint64_t n = std::min(slice, n_words - off);
+    uint64_t* mine = (uint64_t*)c->filt.blocks + off;
+    const ncclResult_t r = g.api.AllGather(mine, c->comm_tmp.p, n * 8, ncclUint8, g.comm, s);
+    if (r != ncclSuccess) {
+      return c->fail_nccl(r, "ncclAllGather (bit vector)");
+    }
+    k_or_gathered<<<grid_for(n, 256, c->sm_count * 8), 256, 0, s>>>(mine, c->comm_tmp.p, n, n,
+                                                                    g.rank, g.world);
+    n_launch += 2;
+  }
+  c->kend(GRB_K_GATHER, n_launch);
   GRB_CUDA(c, cudaGetLastError());
   return GRB_OK;
 }
@@ -937,7 +1152,49 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
 int
 grb_build_bitvector(grb_ctx* c)
 {
-  return grb_build_bitvector_range(c, 0, c->n_reads);
+  if (!c->comm) {
+    return grb_build_bitvector_range(c, 0, c->n_reads);
+  }
+  // equal shares of the flagged bases, cut at read boundaries (every rank computes the same cut)
+  uint64_t total = 0;
+  for (uint64_t r = 0; r < c->n_reads; ++r) {
+    total += (c->h_flags[r] & GRB_READ_PASS1) ? c->h_len[r] : 0;
+  }
+  const int W = c->comm->world, me = c->comm->rank;
+  uint64_t lo = c->n_reads, hi = c->n_reads, acc = 0;
+  const uint64_t b_lo = total / W * me + std::min<uint64_t>(me, total % W);
+  const uint64_t b_hi = total / W * (me + 1) + std::min<uint64_t>(me + 1, total % W);
+  for (uint64_t r = 0; r < c->n_reads; ++r) {
+    if (lo == c->n_reads && acc >= b_lo) {
+      lo = r;
+    }
+    if (acc >= b_hi) {
+      hi = r;
+      break;
+    }
+    acc += (c->h_flags[r] & GRB_READ_PASS1) ? c->h_len[r] : 0;
+  }
+  if (me == W - 1) {
+    hi = c->n_reads;
+  }
+  if (lo > hi) {
+    lo = hi;
+  }
+  cudaEvent_t t0 = c->prof_event();
+  cudaEventRecord(t0, c->stream);
+  int rc = grb_build_bitvector_range(c, lo, hi - lo);
+  if (rc == GRB_OK) {
+    rc = or_reduce_bitvector(c);
+  }
+  if (rc == GRB_OK) { // device time of the whole phase, exchange included
+    cudaEventRecord(c->ev1, c->stream);
+    cudaEventSynchronize(c->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, t0, c->ev1);
+    c->last_ms = ms;
+  }
+  c->prof_free.push_back(t0);
+  return rc;
 }
 
 int
@@ -1624,7 +1881,7 @@ launch_batch2(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   c->launches += 1;
   c->kbegin();
   k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
-    c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state);
+    c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state, 0u, b.n_bt);
   c->kend(GRB_K_QUERY);
   c->kbegin();
   k2_cmat<256><<<b.nb, 256, cmat_smem, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state, n_cap, us,
@@ -1804,10 +2061,47 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   GRB_CUDA(c, cudaMemsetAsync(b3.barrier, 0, 8, s));
   k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
   c->launches += 1;
-  c->kbegin();
-  k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
-    c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state);
-  c->kend(GRB_K_QUERY);
+  if (!c->comm) {
+    c->kbegin();
+    k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
+      c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state, 0u, b.n_bt);
+    c->kend(GRB_K_QUERY);
+  } else {
+    // W GPUs: this rank's share of the batch's tiles, then one NCCL group gathers every per-tile
+    // output in place (the buffers are sized for W * chunk tiles, grb_select_reads)
+    GrbComm& g = *c->comm;
+    const GrbShare sh = grb_share(b.n_bt, g.rank, g.world);
+    c->kbegin();
+    if (sh.hi > sh.lo) {
+      k2_query<512><<<grid_for(sh.hi - sh.lo, 1, 1u << 20), 512, c->query_smem, s>>>(
+        c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state, (uint32_t)sh.lo,
+        (uint32_t)sh.hi);
+    }
+    c->kend(GRB_K_QUERY, sh.hi > sh.lo ? 1 : 0);
+    c->kbegin();
+    const uint64_t ts = c->prm.table_size;
+    struct Piece
+    {
+      void* base;
+      uint64_t bytes_per_tile;
+    };
+    const Piece pieces[] = { { bd.stash, T * h * 8 },  { b2.vk, ts * 4 },        { b2.vc, ts * 4 },
+                             { bd.best_id, 4 },        { bd.best_count, 4 },     { bd.tile_hits, 4 },
+                             { bd.tile_miss, 4 } };
+    ncclResult_t r = g.api.GroupStart();
+    for (const Piece& pc : pieces) {
+      if (r != ncclSuccess) {
+        break;
+      }
+      const uint64_t n = sh.chunk * pc.bytes_per_tile;
+      r = g.api.AllGather((const char*)pc.base + (uint64_t)g.rank * n, pc.base, n, ncclUint8, g.comm, s);
+    }
+    const ncclResult_t r2 = g.api.GroupEnd();
+    if (r != ncclSuccess || r2 != ncclSuccess) {
+      return c->fail_nccl(r != ncclSuccess ? r : r2, "ncclAllGather (batch query results)");
+    }
+    c->kend(GRB_K_GATHER, 1);
+  }
   c->kbegin();
   k2_cmat<256><<<b.nb, 256, cmat_smem, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state, n_cap, us,
                                            cm_smem);
@@ -1932,8 +2226,10 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       }
       if (!bp.batches.empty()) {
         bp.tile_first.push_back(bp.batches.back().n_bt);
+        // with W ranks every per-tile buffer holds W equal shares (the last one padded)
+        const uint64_t pad_bt = c->comm ? (uint64_t)c->comm->world : 0;
         rc = c->batch_ver == 3
-               ? batch3_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_nb)
+               ? batch3_prepare(c, std::max<uint64_t>(max_bt, 1) + pad_bt, max_len / T, max_cm, max_nb)
                : c->batch_ver == 2
                    ? batch2_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_nb)
                    : batch_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_dd);

@@ -120,7 +120,8 @@ grb2_vote_add(uint32_t* vk, uint32_t* vc, uint32_t mask, uint32_t id, uint32_t d
 template<int BS>
 __global__ void __launch_bounds__(BS)
 k2_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilterDev filt,
-         GrbSelParams prm, GrbBatchDev bd, GrbB2 b2, const GrbSelState* __restrict__ state)
+         GrbSelParams prm, GrbBatchDev bd, GrbB2 b2, const GrbSelState* __restrict__ state,
+         uint32_t bt_lo, uint32_t bt_hi)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GrbSeedTables& st = *reinterpret_cast<GrbSeedTables*>(smem_raw);
@@ -139,7 +140,9 @@ k2_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilter
   const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
   const uint32_t tmask = prm.table_size - 1;
 
-  for (uint32_t bt = blockIdx.x; bt < bd.n_bt; bt += gridDim.x) {
+  // tiles [bt_lo, bt_hi) of the batch: the whole batch on one GPU, this rank's share on several
+  // (the per-tile outputs are all-gathered afterwards, comm.cuh)
+  for (uint32_t bt = bt_lo + blockIdx.x; bt < bt_hi; bt += gridDim.x) {
     const uint32_t b = bd.tile_read[bt];
     const uint32_t t = bt - bd.tile_first[b];
     const uint64_t read_idx = bd.read_idx[b];

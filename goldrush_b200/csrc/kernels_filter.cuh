@@ -86,6 +86,190 @@ k_fill_bits(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFil
   }
 }
 
+// ---- partitioned fill: the random read-modify-writes of pass 1 made L2 resident -------------------
+// k_fill_bits above is bound by random atomics over the whole bit vector (measured on B200: about
+// 25 G atomicOr/s once the footprint leaves L2, 190 G/s inside it, profiles/sector_roofline_r01.json).
+// Pass 1 has no order dependence (MIBFConstructSupport.hpp:134-147 is a commutative OR), so the
+// positions of a round of reads are first bucketed by filter partition (2^pshift bits, about 22 MB
+// of blocks: a fraction of the 126 MB L2) and then applied partition by partition:
+//   k_fill_part   CTA per 2048 read positions: hash, bucket in shared memory, append each bucket
+//                 to its partition's list with one global reservation per (CTA, partition) and
+//                 coalesced 4-byte offsets                               [streaming writes]
+//   k_fill_apply  partition-major sweep over the lists: atomicOr into blocks that stay in L2
+// A list that overflows its capacity falls back to the direct atomicOr (always correct).
+#define GRB_PART_MAX 512     // partitions a CTA can scan (one thread each)
+#define GRB_PART_H 4         // patterns the register-resident bucketing is unrolled for
+#define GRB_APPLY_TILE 8192u // list entries per CTA step of k_fill_apply
+
+struct GrbFillPart
+{
+  uint32_t* lists;   // [n_part * cap] offsets within the partition
+  uint32_t* cursor;  // [n_part] entries reserved (may exceed cap: the excess went the direct way)
+  uint32_t n_part;
+  uint32_t pshift;   // partition = pos >> pshift
+  uint32_t cap;      // list capacity, entries
+  uint32_t pad;
+};
+
+__device__ __forceinline__ void
+grb_set_bit_pos(const GrbFilterDev& f, uint64_t pos)
+{
+  const uint64_t blk = grb_div3(pos >> 6);
+  const unsigned r = (unsigned)(pos - blk * GRB_BLK_BITS);
+  atomicOr(reinterpret_cast<unsigned long long*>(f.blocks + blk * 4 + 1 + (r >> 6)),
+           1ull << (r & 63));
+}
+
+// Dynamic shared memory: uint32 stage[GRB_FILL_CHUNK * h] | hist[n_part] | sbase[n_part + 1] |
+// gbase[n_part]
+template<int BS>
+__global__ void __launch_bounds__(BS)
+k_fill_part(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilterDev filt,
+            const uint32_t* __restrict__ chunk_read, const uint64_t* __restrict__ chunk_first,
+            uint64_t chunk0, uint64_t n_chunks, GrbFillPart fp)
+{
+  constexpr int PER = GRB_FILL_CHUNK / BS;
+  __shared__ GrbSeedTables st;
+  __shared__ uint64_t sw[GRB_FILL_CHUNK / 32 + 8];
+  __shared__ uint64_t s_fr[GRB_FILL_CHUNK + GRB_MAX_SPAN];
+  __shared__ uint64_t s_rr[GRB_FILL_CHUNK + GRB_MAX_SPAN];
+  __shared__ uint32_t s_total;
+  extern __shared__ __align__(16) uint32_t fill_dyn[];
+  for (unsigned i = threadIdx.x; i < sizeof(GrbSeedTables) / 8; i += BS) {
+    reinterpret_cast<uint64_t*>(&st)[i] = reinterpret_cast<const uint64_t*>(seeds_g)[i];
+  }
+  __syncthreads();
+  const unsigned half = st.half, k = st.k, h = st.h;
+  const uint32_t P = fp.n_part;
+  uint32_t* stage = fill_dyn;
+  uint32_t* hist = stage + GRB_FILL_CHUNK * h;
+  uint32_t* sbase = hist + P;
+  uint32_t* gbase = sbase + P + 1;
+  const uint32_t omask = (1u << fp.pshift) - 1u;
+
+  for (uint64_t c = chunk0 + blockIdx.x; c < chunk0 + n_chunks; c += gridDim.x) {
+    const uint32_t r = chunk_read[c];
+    const uint32_t len = reads.len[r];
+    const uint32_t p0 = (uint32_t)(c - chunk_first[r]) * GRB_FILL_CHUNK;
+    const uint64_t w_read = reads.word_off[r];
+    const uint32_t w_first = p0 >> 5;
+    const uint32_t w_total = (len + 31) / 32;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < GRB_FILL_CHUNK / 32 + 8; i += BS) {
+      sw[i] = (w_first + i < w_total) ? reads.bases[w_read + w_first + i] : 0ull;
+    }
+    for (unsigned i = threadIdx.x; i < P; i += BS) {
+      hist[i] = 0;
+    }
+    __syncthreads();
+    const unsigned n_half = GRB_FILL_CHUNK + half + h;
+    uint64_t fl[PER], rl[PER];
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const unsigned j = it * BS + threadIdx.x;
+      const GrbWindow w = grb_window([&](uint64_t wi) { return sw[wi]; }, (uint64_t)(p0 & 31) + j);
+      const GrbHalf hh = grb_half_hashes(st, w);
+      fl[it] = hh.fl;
+      rl[it] = hh.rl;
+      s_fr[j] = hh.fr;
+      s_rr[j] = hh.rr;
+    }
+    for (unsigned j = GRB_FILL_CHUNK + threadIdx.x; j < n_half; j += BS) {
+      const GrbWindow w = grb_window([&](uint64_t wi) { return sw[wi]; }, (uint64_t)(p0 & 31) + j);
+      const GrbHalf hh = grb_half_hashes(st, w);
+      s_fr[j] = hh.fr;
+      s_rr[j] = hh.rr;
+    }
+    __syncthreads();
+    // bucket: partition, offset and the rank inside this CTA's bucket stay in registers
+    uint32_t off[PER][GRB_PART_H], plr[PER][GRB_PART_H]; // plr = partition << 16 | rank in bucket
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const unsigned j = it * BS + threadIdx.x;
+      const uint64_t pos_in_read = (uint64_t)p0 + j;
+#pragma unroll
+      for (int i = 0; i < GRB_PART_H; ++i) {
+        plr[it][i] = 0xFFFFFFFFu;
+        if (i < (int)h && pos_in_read + k + i <= len) {
+          const uint64_t hv = grb_combine(i, fl[it], rl[it], s_fr[j + half + i], s_rr[j + half + i]);
+          const uint64_t pos = grb_fastmod(hv, filt.bits, filt.inv);
+          const uint32_t p = (uint32_t)(pos >> fp.pshift);
+          off[it][i] = (uint32_t)pos & omask;
+          plr[it][i] = (p << 16) | atomicAdd(&hist[p], 1u); // at most 2048 * 4 entries per bucket
+        }
+      }
+    }
+    __syncthreads();
+    // local exclusive scan of the bucket sizes + one global reservation per non-empty bucket
+    {
+      const uint32_t mine = threadIdx.x < P ? hist[threadIdx.x] : 0u;
+      uint32_t total;
+      const uint32_t ex = grb_block_excl_scan<BS>(mine, &total);
+      if (threadIdx.x < P) {
+        sbase[threadIdx.x] = ex;
+        gbase[threadIdx.x] = mine ? atomicAdd(&fp.cursor[threadIdx.x], mine) : 0u;
+      }
+      if (threadIdx.x == 0) {
+        sbase[P] = total;
+        s_total = total;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+#pragma unroll
+      for (int i = 0; i < GRB_PART_H; ++i) {
+        if (plr[it][i] != 0xFFFFFFFFu) {
+          stage[sbase[plr[it][i] >> 16] + (plr[it][i] & 0xFFFFu)] = off[it][i];
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t total = s_total;
+    for (uint32_t idx = threadIdx.x; idx < total; idx += BS) {
+      uint32_t lo = 0, hi = P; // last p with sbase[p] <= idx
+      while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sbase[mid] <= idx) {
+          lo = mid;
+        } else {
+          hi = mid;
+        }
+      }
+      const uint32_t g = gbase[lo] + (idx - sbase[lo]);
+      const uint32_t o = stage[idx];
+      if (g < fp.cap) {
+        fp.lists[(uint64_t)lo * fp.cap + g] = o;
+      } else {
+        grb_set_bit_pos(filt, ((uint64_t)lo << fp.pshift) | o);
+      }
+    }
+  }
+}
+
+// Partition-major sweep: CTAs take list tiles in increasing (partition, offset) order, so at any
+// moment the whole GPU works inside one or two partitions and their blocks stay in L2.
+__global__ void __launch_bounds__(256)
+k_fill_apply(GrbFilterDev filt, GrbFillPart fp)
+{
+  const uint32_t tiles_per_part = (fp.cap + GRB_APPLY_TILE - 1) / GRB_APPLY_TILE;
+  const uint64_t n_tiles = (uint64_t)fp.n_part * tiles_per_part;
+  for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const uint32_t p = (uint32_t)(t / tiles_per_part);
+    const uint32_t i0 = (uint32_t)(t - (uint64_t)p * tiles_per_part) * GRB_APPLY_TILE;
+    const uint32_t n = min(__ldg(&fp.cursor[p]), fp.cap);
+    if (i0 >= n) {
+      continue;
+    }
+    const uint32_t i1 = min(i0 + GRB_APPLY_TILE, n);
+    const uint32_t* list = fp.lists + (uint64_t)p * fp.cap;
+    const uint64_t base = (uint64_t)p << fp.pshift;
+    for (uint32_t i = i0 + threadIdx.x; i < i1; i += 256) {
+      grb_set_bit_pos(filt, base | __ldcs(&list[i]));
+    }
+  }
+}
+
 // ---- rank build: per-block popcounts -> exclusive scan -> word 0 of every block ----
 #define GRB_RANK_ITEMS 8
 

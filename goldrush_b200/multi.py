@@ -9,7 +9,10 @@ What shards (SURVEY.md 8e / DESIGN.md 6):
   them locally (`or_allreduce`); on a GPU the local OR is the library's `grb_or_words` kernel.
 * pass 2 speculative query (goldrush_path.cpp:544-626): the tiles of one batch are cut into W equal
   chunks (`tile_chunk`), rank r queries chunk r inside `grb_select_reads`, and the per-tile results
-  are all-gathered over NVLink by the library's own NCCL communicator (`init_comm`).
+  are all-gathered over NVLink by the library's own NCCL communicator (`init_comm`, csrc/comm.cuh).
+  With that communicator in place `grb_build_bitvector` also shards and OR-reduces pass 1 natively;
+  `or_allreduce` / `build_bitvector_sharded` below remain for callers that bring their own
+  collectives (and for the gloo tests).
 * the ordered commit (goldrush_path.cpp:1229-1256) does not shard: it is replicated, integer-only and
   deterministic, so every replica ends each batch with the same filter and the same decisions
   (`assert_replicas_agree`).
@@ -85,18 +88,23 @@ def build_bitvector_sharded(eng, n_reads, device, stream, group=None):
     eng.sync()
 
 
-def init_comm(eng, group=None):
-    """Creates the library's NCCL communicator for the pass-2 all-gather: rank 0 makes the NCCL
-    unique id, torch.distributed carries it to the other ranks (works over nccl or gloo)."""
+def init_comm(device, group=None, api=None):
+    """Creates the library's process-wide NCCL communicator (one process per GPU): rank 0 makes the
+    NCCL unique id, torch.distributed carries it to the other ranks (works over nccl or gloo).
+    Call before creating the Engine / calling run_path; returns (rank, world).  `api` is the
+    module providing comm_unique_id / comm_init (goldrush_b200.api; injectable for CPU tests)."""
+    if api is None:
+        from . import api
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if world == 1:
-        return
-    ident = eng.comm_unique_id() if rank == 0 else bytes(128)
-    dev = torch.device("cuda", eng.device) if dist.get_backend(group) == "nccl" else "cpu"
+        return rank, world
+    ident = api.comm_unique_id() if rank == 0 else bytes(128)
+    dev = torch.device("cuda", device) if dist.get_backend(group) == "nccl" else "cpu"
     t = torch.tensor(list(ident), dtype=torch.uint8, device=dev)
     dist.broadcast(t, src=0, group=group)
-    eng.comm_init(bytes(t.cpu().tolist()), rank, world)
+    api.comm_init(bytes(t.cpu().tolist()), rank, world, device)
+    return rank, world
 
 
 def assert_replicas_agree(decisions, group=None):

@@ -209,8 +209,26 @@ int grb_query_read(grb_ctx* ctx, uint64_t read_idx, uint32_t* best_id, uint32_t*
 int grb_insert_tiles(grb_ctx* ctx, uint64_t read_idx, uint32_t tile_start, uint32_t tile_end,
                      uint32_t id);
 
-/* ---- multi-GPU plumbing (one process per GPU; collectives are issued by the caller, e.g.
- * torch.distributed / NCCL, on the raw device pointers) ---- */
+/* ---- multi-GPU: one process per GPU, the filter replicated on every rank ----
+ * A process-wide NCCL communicator, bound at run time (dlopen of libnccl.so.2; no link dependency).
+ * Rank 0 calls grb_comm_unique_id and ships the 128 bytes to the other ranks by any means
+ * (torch.distributed broadcast, MPI, a file); every rank then calls grb_comm_init on its device.
+ * Contexts created afterwards on that device shard the two phases that shard:
+ *   grb_build_bitvector  - pass 1 over this rank's share of the reads + OR-reduce of the vectors
+ *                          (replaces the OpenMP team of fill_bit_vector, goldrush_path.cpp:252-311)
+ *   grb_select_reads     - the speculative query of each batch over this rank's share of its
+ *                          tiles + all-gather of the per-tile results; the ordered commit is
+ *                          replicated, so every rank returns the same decisions
+ * and grb_run_path inherits both.  GRB_COMM=0 in the environment keeps contexts single-GPU.
+ * Errors of grb_comm_unique_id / grb_comm_init are reported by grb_last_error(NULL). */
+int grb_comm_unique_id(uint8_t* out128);
+int grb_comm_init(const uint8_t* id128, int rank, int world, int device);
+void grb_comm_destroy(void);
+/* ctx == NULL: the process-wide communicator; else what this context uses (0 / 1 if unsharded) */
+int grb_comm_info(const grb_ctx* ctx, int* rank, int* world);
+
+/* ---- plumbing for callers that issue their own collectives (e.g. torch.distributed) on the raw
+ * device pointers ---- */
 int grb_bitvector_device(grb_ctx* ctx, void** dev_ptr, uint64_t* bytes);
 /* dst |= src on this context's stream, n 8-byte words, both DEVICE pointers */
 int grb_or_words(grb_ctx* ctx, void* dst, const void* src, uint64_t n_words);
@@ -232,7 +250,8 @@ typedef enum grb_kernel_class
   GRB_K_SMOOTH = 5, /*         k_spec_cmat: count matrix + smoothing on the speculative votes */
   GRB_K_DEDUPE = 6, /*         k_spec_dedupe: distinct ranks per read for the insert */
   GRB_K_COMMIT = 7, /* K4c     k_commit_batch: ordered re-validation, decision and insert */
-  GRB_K_COUNT = 8
+  GRB_K_GATHER = 8, /*         multi-GPU exchange: NCCL all-gathers + k_or_gathered (0 on one GPU) */
+  GRB_K_COUNT = 9
 } grb_kernel_class;
 int grb_profile_enable(grb_ctx* ctx, int on);
 /* phase clocks of the ordered commit kernel since the last grb_filter_alloc, as counted by its

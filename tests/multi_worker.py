@@ -1,0 +1,97 @@
+"""One rank of the multi-GPU parity run (launched by tests/test_gpu_multi.py through torchrun, one
+process per GPU).  Every rank runs the same golden cases through grb_run_path with the library's NCCL
+communicator in place (pass 1 sharded + OR-reduced, each batch's query sharded + all-gathered,
+commit replicated) and writes the digests of ITS OWN output files; the test compares every rank's
+digests with the reference fixtures.  Also checks, at the engine level, that the OR-reduced bit
+vector and the decisions equal those of an unsharded context on the same GPU."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import goldrush_b200 as grb  # noqa: E402
+from goldrush_b200 import multi  # noqa: E402
+import parity_util as pu  # noqa: E402
+from test_gpu_parity import _args_to_params, SEED22  # noqa: E402
+
+CASES = ["silver_default", "small_tiles_random_seed", "golden_lognormal_all_lengths", "ragged_tail_h4"]
+
+
+def main():
+    out_dir = sys.argv[1]
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")  # only carries the NCCL unique id and the barriers
+    result = {"rank": rank, "world": world, "cases": {}}
+
+    # ---- unsharded reference on this GPU, before the communicator exists ----
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, 3)
+    sp = grb.api.synth_params(300000, 12.0, 5000, 77)
+    data = grb.synth_fastq(sp)
+    kw = dict(genome_size=300000, weight=16, tile_length=250, min_length=5000, silver_path=1,
+              max_paths=3, ratio=0.9, device=local)
+
+    def engine_run():
+        with grb.Engine(seeds, **kw) as e:
+            e.reads_ingest_fastq(data)
+            n = e.reads_count()
+            e.reads_set_flags(np.full(n, 3, dtype=np.uint8))
+            e.filter_alloc(grb.calc_optimal_size(grb.default_hash_universe(16, 300000, 3), 1, 0.1))
+            e.build_bitvector()
+            bits = e.copy_bitvector()
+            pop = e.finalize_bitvector()
+            dec, stats, fin = e.select_reads_array()
+            return bits, pop, dec.copy(), grb.api.comm_info(e), e.kernel_time("gather")[1]
+
+    bits1, pop1, dec1, info1, _ = engine_run()
+    assert info1 == (0, 1)
+
+    assert multi.init_comm(local) == (rank, world)
+    assert grb.api.comm_info() == (rank, world)
+    bitsw, popw, decw, infow, _ = engine_run()
+    assert infow == (rank, world)
+    result["engine"] = {"bits_equal": bool(np.array_equal(bits1, bitsw)), "pop_equal": pop1 == popw,
+                        "dec_equal": bool(np.array_equal(dec1.view(np.uint8), decw.view(np.uint8))),
+                        "selected": int(((decw["verdict"] == 2) | (decw["verdict"] == 3)).sum())}
+    multi.assert_replicas_agree(decw.view(np.uint8))
+
+    # ---- golden cases through the whole-stage call ----
+    work = os.path.join(out_dir, f"rank{rank}")
+    os.makedirs(work, exist_ok=True)
+    produced = {}
+
+    def outputs_for(case, workdir):
+        if case["name"] not in produced:
+            inp, extra = pu.make_input(case, workdir, outputs_for)
+            with open(inp, "rb") as f:
+                fq = f.read()
+            prefix = os.path.join(workdir, case["name"] + ".gpu")
+            res = grb.run_path(fq, input_path=inp, prefix=prefix, quiet=True, device=local,
+                               **_args_to_params(case["args"] + extra))
+            outs = sorted((os.path.join(workdir, fn) for fn in os.listdir(workdir)
+                           if fn.startswith(os.path.basename(prefix))), key=lambda p: (len(p), p))
+            produced[case["name"]] = (outs, res)
+        return produced[case["name"]][0]
+
+    for name in CASES:
+        outs = outputs_for(pu.case_by_name(name), work)
+        res = produced[name][1]
+        result["cases"][name] = {"outputs": pu.digest_outputs(outs), "filter_bits": res.filter_bits,
+                                 "num_passed_reads": res.num_passed_reads, "launches": res.launches}
+        dist.barrier()
+
+    grb.api.comm_destroy()
+    with open(os.path.join(out_dir, f"result{rank}.json"), "w") as f:
+        json.dump(result, f)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -123,6 +123,28 @@ def test_bitvector_and_rank_match_oracle(h, bits):
             assert (rr, bb) == (er, eb), p
 
 
+@pytest.mark.parametrize("h,bits,env", [
+    (3, 1000000 + 64, {"GRB_FILL_PSHIFT": "16"}),                       # 16 partitions
+    (3, 1000000 + 64, {"GRB_FILL_PSHIFT": "16", "GRB_FILL_BS": "512"}),
+    (1, 333376, {"GRB_FILL_PSHIFT": "12"}),                             # 82 partitions
+    (4, 5000000 + 128, {"GRB_FILL_PSHIFT": "14"}),                      # 306 -> folded to 153
+    (3, 1000000 + 64, {"GRB_FILL_PSHIFT": "16", "GRB_FILL_CAP": "300"}),  # lists overflow
+    (2, 700032, {}),                                                    # one partition
+])
+def test_partitioned_fill_equals_oracle(h, bits, env, monkeypatch):
+    """Pass 1 through the L2-partitioned fill (k_fill_part + k_fill_apply), forced on small filters:
+    the same bit vector as MIBFConstructSupport::insertBV, including the list-overflow fallback."""
+    monkeypatch.setenv("GRB_FILL", "part")
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, h)
+    rng = np.random.default_rng(300 + h)
+    e, f, recs = _build_pair(rng, 60, 30, 9000, seeds, bits)
+    with e:
+        assert np.array_equal(e.copy_bitvector(), f.words())
+        assert e.finalize_bitvector() == f.setup()
+
+
 def _tile_hashes(seq, t, T, k, seeds):
     tile = seq[t * T:t * T + T + k - 1]
     return ou.hash_sequence(tile, seeds)

@@ -57,18 +57,16 @@ def _worker(rank, world, port, out_dir):
             multi.assert_replicas_agree(np.arange(12, dtype=np.uint32) + rank)
 
         # the unique-id broadcast carries 128 bytes from rank 0
-        class FakeEngine:
-            device = 0
-
+        class FakeApi:
             def comm_unique_id(self):
                 return bytes(range(128))
 
-            def comm_init(self, ident, r, w):
-                self.got = (ident, r, w)
+            def comm_init(self, ident, r, w, device):
+                self.got = (ident, r, w, device)
 
-        fe = FakeEngine()
-        multi.init_comm(fe)
-        assert fe.got == (bytes(range(128)), rank, world)
+        fa = FakeApi()
+        assert multi.init_comm(0, api=fa) == (rank, world)
+        assert fa.got == (bytes(range(128)), rank, world, 0)
         with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
             f.write("ok")
     finally:
