@@ -155,6 +155,8 @@ struct grb_ctx
 
   GrbSeedTables h_seed{};
   GrbSeedTables* d_seed = nullptr;
+  ulonglong2* d_gtab = nullptr; // grouped half-hash tables: L[ng * 256] then R[ng * 256]
+  uint32_t gt_groups = 0;
 
   // ---- read store ----
   uint64_t n_reads = 0;
@@ -391,6 +393,28 @@ build_seed_tables(grb_ctx* c)
   return GRB_OK;
 }
 
+// grouped half-hash tables (nthash.cuh): entry [g][v] XORs the contributions of the care positions
+// whose window offset lies in [4g, 4g + 4), for the 4 bases encoded in byte v
+std::vector<ulonglong2>
+build_group_tables(const GrbSeedTables& t, uint32_t* n_groups)
+{
+  const uint32_t ng = (t.half + 3) / 4;
+  std::vector<ulonglong2> tab((size_t)2 * ng * 256, make_ulonglong2(0, 0));
+  for (uint32_t j = 0; j < t.n_care; ++j) {
+    const bool left = j < t.n_left;
+    const uint32_t o = left ? t.care[j] : t.care[j] - t.half;
+    const uint32_t g = o / 4, sh = 2 * (o % 4);
+    ulonglong2* dst = tab.data() + (size_t)(left ? 0 : ng) * 256 + (size_t)g * 256;
+    for (uint32_t v = 0; v < 256; ++v) {
+      const uint32_t b = (v >> sh) & 3u;
+      dst[v].x ^= t.fwd[j][b];
+      dst[v].y ^= t.rev[j][b];
+    }
+  }
+  *n_groups = ng;
+  return tab;
+}
+
 inline unsigned
 grid_for(uint64_t n, unsigned bs, unsigned cap)
 {
@@ -529,6 +553,14 @@ grb_create(const grb_params* p, grb_ctx** out)
         cudaSuccess) {
     return bail(GRB_ERR_CUDA, std::string("seed table upload: ") + cudaGetErrorString(e));
   }
+  {
+    const std::vector<ulonglong2> gt = build_group_tables(c->h_seed, &c->gt_groups);
+    if ((e = grb_pool_alloc((void**)&c->d_gtab, gt.size() * sizeof(ulonglong2))) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_gtab, gt.data(), gt.size() * sizeof(ulonglong2),
+                        cudaMemcpyHostToDevice)) != cudaSuccess) {
+      return bail(GRB_ERR_CUDA, std::string("group table upload: ") + cudaGetErrorString(e));
+    }
+  }
   // 10^(-q/10) with glibc pow, indexed by the raw quality byte (calc_phred_average.cpp:17-20;
   // `char` is signed on this platform, as in the reference build)
   double tab[256];
@@ -557,6 +589,7 @@ grb_destroy(grb_ctx* c)
   grb_pool_free(c->filt.slots);
   grb_pool_free(c->d_state);
   grb_pool_free(c->d_seed);
+  grb_pool_free(c->d_gtab);
   if (c->ev0) {
     cudaEventDestroy(c->ev0);
   }
@@ -1042,7 +1075,16 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
         pshift = (uint32_t)v;
       }
     }
-    while (((c->filt.bits + (1ull << pshift) - 1) >> pshift) > 256) {
+    const char* bs_env = getenv("GRB_FILL_BS");
+    const bool bs512 = bs_env && strcmp(bs_env, "512") == 0;
+    uint64_t part_limit = 1024;
+    if (const char* e = getenv("GRB_FILL_MAXPART")) {
+      const long v = strtol(e, nullptr, 10);
+      if (v >= 1 && (uint64_t)v <= part_limit) {
+        part_limit = (uint64_t)v;
+      }
+    }
+    while (((c->filt.bits + (1ull << pshift) - 1) >> pshift) > part_limit) {
       ++pshift;
     }
     const uint32_t n_part = (uint32_t)((c->filt.bits + (1ull << pshift) - 1) >> pshift);
@@ -1084,33 +1126,35 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
         }
       }
       GRB_CUDA(c, c->fill_lists.reserve(cap * n_part, 0, s));
-      GRB_CUDA(c, c->fill_cursor.reserve(n_part, 0, s));
+      GRB_CUDA(c, c->fill_cursor.reserve(n_part + 1, 0, s));
       GrbFillPart fp{ c->fill_lists.p, c->fill_cursor.p, n_part, pshift, (uint32_t)cap, 0 };
-      const size_t dyn = ((size_t)GRB_FILL_CHUNK * h + 3 * (size_t)n_part + 1) * 4;
-      const int smem_optin = (int)(((size_t)GRB_FILL_CHUNK * GRB_PART_H + 3 * 512 + 1) * 4);
+      const size_t dyn = (size_t)c->gt_groups * 256 * 32 +
+                         ((size_t)(bs512 ? 1024 : GRB_FILL_CHUNK) * h + 3 * (size_t)n_part + 1) * 4;
+      const int smem_optin = (int)((size_t)GRB_MAX_GROUPS * 256 * 32 +
+                                   ((size_t)GRB_FILL_CHUNK * GRB_PART_H + 3 * 1024 + 1) * 4);
       if (!c->fill_attr) {
-        GRB_CUDA(c, cudaFuncSetAttribute(k_fill_part<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GRB_CUDA(c, cudaFuncSetAttribute(k_fill_part<1024, 2048, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_optin));
-        GRB_CUDA(c, cudaFuncSetAttribute(k_fill_part<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        GRB_CUDA(c, cudaFuncSetAttribute(k_fill_part<512, 1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_optin));
         c->fill_attr = true;
       }
       // one 1024-thread CTA per SM at 64 registers, or (GRB_FILL_BS=512) one 512-thread CTA at 106
-      const char* bs_env = getenv("GRB_FILL_BS");
-      const bool bs512 = bs_env && strcmp(bs_env, "512") == 0;
       c->kbegin();
       uint64_t n_launch = 0;
       for (uint64_t c0 = 0; c0 < chunk_read.size(); c0 += round_chunks) {
         const uint64_t nc = std::min<uint64_t>(round_chunks, chunk_read.size() - c0);
-        GRB_CUDA(c, cudaMemsetAsync(fp.cursor, 0, (size_t)n_part * 4, s));
+        GRB_CUDA(c, cudaMemsetAsync(fp.cursor, 0, ((size_t)n_part + 1) * 4, s));
         if (bs512) {
-          k_fill_part<512><<<grid_for(nc, 1, c->sm_count * 4), 512, dyn, s>>>(
-            c->reads_dev(), c->d_seed, c->filt, c->d_chunk_read.p, c->d_chunk_first.p, c0, nc, fp);
+          k_fill_part<512, 1024, 2><<<grid_for(nc * 2, 1, c->sm_count * 8), 512, dyn, s>>>(
+            c->reads_dev(), c->d_seed, c->d_gtab, c->gt_groups, c->filt, c->d_chunk_read.p,
+            c->d_chunk_first.p, c0, nc, fp);
         } else {
-          k_fill_part<1024><<<grid_for(nc, 1, c->sm_count * 4), 1024, dyn, s>>>(
-            c->reads_dev(), c->d_seed, c->filt, c->d_chunk_read.p, c->d_chunk_first.p, c0, nc, fp);
+          k_fill_part<1024, 2048, 1><<<grid_for(nc, 1, c->sm_count * 4), 1024, dyn, s>>>(
+            c->reads_dev(), c->d_seed, c->d_gtab, c->gt_groups, c->filt, c->d_chunk_read.p,
+            c->d_chunk_first.p, c0, nc, fp);
         }
-        k_fill_apply<<<c->sm_count * 8, 256, 0, s>>>(c->filt, fp);
+        k_fill_apply<<<c->sm_count * 8, 256, ((size_t)n_part + 1) * 4, s>>>(c->filt, fp);
         n_launch += 2;
       }
       c->kend(GRB_K_FILL, n_launch);

@@ -97,14 +97,14 @@ k_fill_bits(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFil
 //                 coalesced 4-byte offsets                               [streaming writes]
 //   k_fill_apply  partition-major sweep over the lists: atomicOr into blocks that stay in L2
 // A list that overflows its capacity falls back to the direct atomicOr (always correct).
-#define GRB_PART_MAX 512     // partitions a CTA can scan (one thread each)
 #define GRB_PART_H 4         // patterns the register-resident bucketing is unrolled for
 #define GRB_APPLY_TILE 8192u // list entries per CTA step of k_fill_apply
 
 struct GrbFillPart
 {
   uint32_t* lists;   // [n_part * cap] offsets within the partition
-  uint32_t* cursor;  // [n_part] entries reserved (may exceed cap: the excess went the direct way)
+  uint32_t* cursor;  // [n_part] entries reserved (may exceed cap: the excess went the direct way);
+                     // [n_part] = ticket counter of k_fill_apply
   uint32_t n_part;
   uint32_t pshift;   // partition = pos >> pshift
   uint32_t cap;      // list capacity, entries
@@ -120,65 +120,77 @@ grb_set_bit_pos(const GrbFilterDev& f, uint64_t pos)
            1ull << (r & 63));
 }
 
-// Dynamic shared memory: uint32 stage[GRB_FILL_CHUNK * h] | hist[n_part] | sbase[n_part + 1] |
-// gbase[n_part]
-template<int BS>
-__global__ void __launch_bounds__(BS)
-k_fill_part(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilterDev filt,
+// Dynamic shared memory: ulonglong2 gL[ng * 256] | gR[ng * 256] | uint32 stage[SUB * h] |
+// hist[n_part] | sbase[n_part + 1] | gbase[n_part]
+// A CTA walks its 2048-position chunk in sub-chunks of SUB positions (BS threads, SUB / BS
+// positions per thread), so that two or three CTAs fit on an SM and overlap each other's barriers.
+template<int BS, int SUB, int MINB>
+__global__ void __launch_bounds__(BS, MINB)
+k_fill_part(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g,
+            const ulonglong2* __restrict__ gtab, uint32_t ng, GrbFilterDev filt,
             const uint32_t* __restrict__ chunk_read, const uint64_t* __restrict__ chunk_first,
             uint64_t chunk0, uint64_t n_chunks, GrbFillPart fp)
 {
-  constexpr int PER = GRB_FILL_CHUNK / BS;
-  __shared__ GrbSeedTables st;
-  __shared__ uint64_t sw[GRB_FILL_CHUNK / 32 + 8];
-  __shared__ uint64_t s_fr[GRB_FILL_CHUNK + GRB_MAX_SPAN];
-  __shared__ uint64_t s_rr[GRB_FILL_CHUNK + GRB_MAX_SPAN];
+  constexpr int PER = SUB / BS;
+  static_assert(GRB_FILL_CHUNK % SUB == 0 && SUB % BS == 0, "sub-chunks tile the chunk");
+  __shared__ uint64_t sw[SUB / 32 + 8];
+  __shared__ uint64_t s_fr[SUB + GRB_MAX_SPAN];
+  __shared__ uint64_t s_rr[SUB + GRB_MAX_SPAN];
   __shared__ uint32_t s_total;
-  extern __shared__ __align__(16) uint32_t fill_dyn[];
-  for (unsigned i = threadIdx.x; i < sizeof(GrbSeedTables) / 8; i += BS) {
-    reinterpret_cast<uint64_t*>(&st)[i] = reinterpret_cast<const uint64_t*>(seeds_g)[i];
+  extern __shared__ __align__(16) unsigned char fill_dyn[];
+  ulonglong2* gL = reinterpret_cast<ulonglong2*>(fill_dyn);
+  ulonglong2* gR = gL + ng * 256;
+  for (unsigned i = threadIdx.x; i < 2 * ng * 256; i += BS) {
+    gL[i] = gtab[i];
   }
-  __syncthreads();
-  const unsigned half = st.half, k = st.k, h = st.h;
+  const unsigned half = seeds_g->half, k = seeds_g->k, h = seeds_g->h;
   const uint32_t P = fp.n_part;
-  uint32_t* stage = fill_dyn;
-  uint32_t* hist = stage + GRB_FILL_CHUNK * h;
+  uint32_t* stage = reinterpret_cast<uint32_t*>(gR + ng * 256);
+  uint32_t* hist = stage + SUB * h;
   uint32_t* sbase = hist + P;
   uint32_t* gbase = sbase + P + 1;
   const uint32_t omask = (1u << fp.pshift) - 1u;
+  constexpr uint64_t SUBS = GRB_FILL_CHUNK / SUB;
+  __syncthreads();
 
-  for (uint64_t c = chunk0 + blockIdx.x; c < chunk0 + n_chunks; c += gridDim.x) {
+  for (uint64_t cs = (chunk0 * SUBS) + blockIdx.x; cs < (chunk0 + n_chunks) * SUBS; cs += gridDim.x) {
+    const uint64_t c = cs / SUBS;
     const uint32_t r = chunk_read[c];
     const uint32_t len = reads.len[r];
-    const uint32_t p0 = (uint32_t)(c - chunk_first[r]) * GRB_FILL_CHUNK;
+    const uint32_t p0 =
+      (uint32_t)(c - chunk_first[r]) * GRB_FILL_CHUNK + (uint32_t)(cs - c * SUBS) * SUB;
+    if (p0 + k > len) { // nothing of this sub-chunk is a valid position (uniform over the CTA)
+      continue;
+    }
     const uint64_t w_read = reads.word_off[r];
     const uint32_t w_first = p0 >> 5;
     const uint32_t w_total = (len + 31) / 32;
     __syncthreads();
-    for (unsigned i = threadIdx.x; i < GRB_FILL_CHUNK / 32 + 8; i += BS) {
+    for (unsigned i = threadIdx.x; i < SUB / 32 + 8; i += BS) {
       sw[i] = (w_first + i < w_total) ? reads.bases[w_read + w_first + i] : 0ull;
     }
     for (unsigned i = threadIdx.x; i < P; i += BS) {
       hist[i] = 0;
     }
     __syncthreads();
-    const unsigned n_half = GRB_FILL_CHUNK + half + h;
+    const unsigned n_half = SUB + half + h;
     uint64_t fl[PER], rl[PER];
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
       const unsigned j = it * BS + threadIdx.x;
-      const GrbWindow w = grb_window([&](uint64_t wi) { return sw[wi]; }, (uint64_t)(p0 & 31) + j);
-      const GrbHalf hh = grb_half_hashes(st, w);
-      fl[it] = hh.fl;
-      rl[it] = hh.rl;
-      s_fr[j] = hh.fr;
-      s_rr[j] = hh.rr;
+      const uint64_t lo = grb_lo64([&](uint64_t wi) { return sw[wi]; }, (uint64_t)(p0 & 31) + j);
+      const ulonglong2 l = grb_group_half(gL, ng, lo);
+      const ulonglong2 rt = grb_group_half(gR, ng, lo);
+      fl[it] = l.x;
+      rl[it] = l.y;
+      s_fr[j] = rt.x;
+      s_rr[j] = rt.y;
     }
-    for (unsigned j = GRB_FILL_CHUNK + threadIdx.x; j < n_half; j += BS) {
-      const GrbWindow w = grb_window([&](uint64_t wi) { return sw[wi]; }, (uint64_t)(p0 & 31) + j);
-      const GrbHalf hh = grb_half_hashes(st, w);
-      s_fr[j] = hh.fr;
-      s_rr[j] = hh.rr;
+    for (unsigned j = SUB + threadIdx.x; j < n_half; j += BS) {
+      const uint64_t lo = grb_lo64([&](uint64_t wi) { return sw[wi]; }, (uint64_t)(p0 & 31) + j);
+      const ulonglong2 rt = grb_group_half(gR, ng, lo);
+      s_fr[j] = rt.x;
+      s_rr[j] = rt.y;
     }
     __syncthreads();
     // bucket: partition, offset and the rank inside this CTA's bucket stay in registers
@@ -195,23 +207,28 @@ k_fill_part(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFil
           const uint64_t pos = grb_fastmod(hv, filt.bits, filt.inv);
           const uint32_t p = (uint32_t)(pos >> fp.pshift);
           off[it][i] = (uint32_t)pos & omask;
-          plr[it][i] = (p << 16) | atomicAdd(&hist[p], 1u); // at most 2048 * 4 entries per bucket
+          plr[it][i] = (p << 16) | atomicAdd(&hist[p], 1u); // at most SUB * 4 entries per bucket
         }
       }
     }
     __syncthreads();
     // local exclusive scan of the bucket sizes + one global reservation per non-empty bucket
     {
-      const uint32_t mine = threadIdx.x < P ? hist[threadIdx.x] : 0u;
-      uint32_t total;
-      const uint32_t ex = grb_block_excl_scan<BS>(mine, &total);
-      if (threadIdx.x < P) {
-        sbase[threadIdx.x] = ex;
-        gbase[threadIdx.x] = mine ? atomicAdd(&fp.cursor[threadIdx.x], mine) : 0u;
+      uint32_t run = 0;
+      for (uint32_t base = 0; base < P; base += BS) { // P > BS only for the 512-thread CTAs
+        const uint32_t q = base + threadIdx.x;
+        const uint32_t mine = q < P ? hist[q] : 0u;
+        uint32_t total;
+        const uint32_t ex = grb_block_excl_scan<BS>(mine, &total);
+        if (q < P) {
+          sbase[q] = run + ex;
+          gbase[q] = mine ? atomicAdd(&fp.cursor[q], mine) : 0u;
+        }
+        run += total;
       }
       if (threadIdx.x == 0) {
-        sbase[P] = total;
-        s_total = total;
+        sbase[P] = run;
+        s_total = run;
       }
     }
     __syncthreads();
@@ -247,25 +264,73 @@ k_fill_part(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFil
   }
 }
 
-// Partition-major sweep: CTAs take list tiles in increasing (partition, offset) order, so at any
-// moment the whole GPU works inside one or two partitions and their blocks stay in L2.
+// Partition-major sweep.  List tiles are handed out in (partition, offset) order through one global
+// ticket counter (fp.cursor[n_part]), so at any moment the whole GPU works inside one or two
+// partitions and their blocks stay in L2 (a static grid-stride let fast CTAs run partitions ahead:
+// ncu showed 30 GB of DRAM traffic per 2 GB of lists).  Dynamic shared memory: uint32 pre[n_part + 1].
 __global__ void __launch_bounds__(256)
 k_fill_apply(GrbFilterDev filt, GrbFillPart fp)
 {
-  const uint32_t tiles_per_part = (fp.cap + GRB_APPLY_TILE - 1) / GRB_APPLY_TILE;
-  const uint64_t n_tiles = (uint64_t)fp.n_part * tiles_per_part;
-  for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const uint32_t p = (uint32_t)(t / tiles_per_part);
-    const uint32_t i0 = (uint32_t)(t - (uint64_t)p * tiles_per_part) * GRB_APPLY_TILE;
-    const uint32_t n = min(__ldg(&fp.cursor[p]), fp.cap);
-    if (i0 >= n) {
-      continue;
+  extern __shared__ uint32_t pre[]; // tiles before partition p
+  __shared__ uint32_t s_ticket;
+  const uint32_t P = fp.n_part;
+  {
+    uint32_t run = 0;
+    for (uint32_t base = 0; base < P; base += 256) {
+      const uint32_t q = base + threadIdx.x;
+      const uint32_t n = q < P ? min(__ldg(&fp.cursor[q]), fp.cap) : 0u;
+      const uint32_t tiles = (n + GRB_APPLY_TILE - 1) / GRB_APPLY_TILE;
+      uint32_t total;
+      const uint32_t ex = grb_block_excl_scan<256>(tiles, &total);
+      if (q < P) {
+        pre[q] = run + ex;
+      }
+      run += total;
     }
+    if (threadIdx.x == 0) {
+      pre[P] = run;
+    }
+  }
+  __syncthreads();
+  const uint32_t n_tiles = pre[P];
+  for (;;) {
+    if (threadIdx.x == 0) {
+      s_ticket = atomicAdd(&fp.cursor[P], 1u);
+    }
+    __syncthreads();
+    const uint32_t t = s_ticket;
+    __syncthreads();
+    if (t >= n_tiles) {
+      break;
+    }
+    uint32_t lo = 0, hi = P; // last p with pre[p] <= t
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (pre[mid] <= t) {
+        lo = mid;
+      } else {
+        hi = mid;
+      }
+    }
+    const uint32_t p = lo;
+    const uint32_t i0 = (t - pre[p]) * GRB_APPLY_TILE;
+    const uint32_t n = min(__ldg(&fp.cursor[p]), fp.cap);
     const uint32_t i1 = min(i0 + GRB_APPLY_TILE, n);
     const uint32_t* list = fp.lists + (uint64_t)p * fp.cap;
     const uint64_t base = (uint64_t)p << fp.pshift;
-    for (uint32_t i = i0 + threadIdx.x; i < i1; i += 256) {
-      grb_set_bit_pos(filt, base | __ldcs(&list[i]));
+    // 8 independent streaming loads, then 8 fire-and-forget atomics (RED) per thread and step
+    for (uint32_t i = i0 + threadIdx.x; i < i1; i += 256 * 8) {
+      uint32_t o[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        o[u] = (i + u * 256 < i1) ? __ldcs(&list[i + u * 256]) : 0xFFFFFFFFu;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (o[u] != 0xFFFFFFFFu) {
+          grb_set_bit_pos(filt, base | o[u]);
+        }
+      }
     }
   }
 }

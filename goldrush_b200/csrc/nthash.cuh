@@ -129,6 +129,47 @@ grb_combine(unsigned i, uint64_t fl, uint64_t rl, uint64_t fr, uint64_t rr)
   return (grb_srol(fl, i) ^ fr) + (rl ^ grb_srol(rr, i));
 }
 
+// ---- grouped half-hash tables ---------------------------------------------------------------------
+// The per-care-position evaluation above costs about 20 instructions per care position (variable
+// 64-bit shifts to pull one base out, two table reads, two 64-bit XORs): ncu showed the fill kernel
+// issue-bound on it.  Both halves only look at window offsets [0, half), so the window is cut into
+// groups of 4 consecutive bases = one byte of the packed window, and a 256-entry table per group
+// holds the XOR of the contributions of every care position inside the group for each of the 256
+// base combinations (don't-care offsets simply do not contribute).  A half hash is then
+// ceil(half / 4) byte extractions and 16-byte table reads:
+//   L[g][v] = { fl, rl } of the left  care positions with offset in [4g, 4g + 4)
+//   R[g][v] = { fr, rr } of the right care positions with offset - half in [4g, 4g + 4)
+// Built on the host from GrbSeedTables (engine.cu, build_group_tables).
+#define GRB_MAX_GROUPS 8 // half <= 32 bases
+
+// the 32 bases starting at absolute base index `pos` (LSB first)
+template<typename WordLoader>
+__device__ __forceinline__ uint64_t
+grb_lo64(WordLoader&& word, uint64_t pos)
+{
+  const uint64_t wi = pos >> 5;
+  const unsigned s = (unsigned)(pos & 31) * 2;
+  const uint64_t w0 = word(wi);
+  return s == 0 ? w0 : ((w0 >> s) | (word(wi + 1) << (64 - s)));
+}
+
+// out.x ^= first halves, out.y ^= second halves of the table entries picked by the window bytes
+__device__ __forceinline__ ulonglong2
+grb_group_half(const ulonglong2* __restrict__ tab, unsigned ng, uint64_t lo)
+{
+  ulonglong2 o = make_ulonglong2(0, 0);
+#pragma unroll
+  for (unsigned g = 0; g < GRB_MAX_GROUPS; ++g) {
+    if (g < ng) {
+      const unsigned v = (unsigned)(lo >> (8 * g)) & 0xFFu;
+      const ulonglong2 e = tab[g * 256 + v];
+      o.x ^= e.x;
+      o.y ^= e.y;
+    }
+  }
+  return o;
+}
+
 // Straightforward evaluation of one pattern at one position (used where the sharing above does
 // not pay, and by the parity export): window starts at the frame position.
 __device__ __forceinline__ uint64_t

@@ -39,11 +39,14 @@ def main():
     bases = int(meta["len"][flags & 1 != 0].sum())
     out = {"workload": wl, "filter_bits": int(bits), "bases_pass1": bases,
            "probes": bases * P["hash_num"], "variants": {}}
-    variants = {"direct": {"GRB_FILL": "direct"},
-                "part_bs1024": {"GRB_FILL": "part"},
-                "part_bs512": {"GRB_FILL": "part", "GRB_FILL_BS": "512"},
-                "part_bs1024_pshift26": {"GRB_FILL": "part", "GRB_FILL_PSHIFT": "26"},
-                "part_bs1024_pshift28": {"GRB_FILL": "part", "GRB_FILL_PSHIFT": "28"}}
+    variants = {"direct": {"GRB_FILL": "direct"}}
+    for ps in (23, 24, 25, 26, 27):
+        variants[f"part_pshift{ps}"] = {"GRB_FILL": "part", "GRB_FILL_PSHIFT": str(ps)}
+        variants[f"part_pshift{ps}_bs512"] = {"GRB_FILL": "part", "GRB_FILL_PSHIFT": str(ps),
+                                             "GRB_FILL_BS": "512"}
+    only = os.environ.get("FILL_AB_ONLY")
+    if only:
+        variants = {k: v for k, v in variants.items() if k in only.split(",")}
     digests = set()
     for name, env in variants.items():
         for k in ("GRB_FILL", "GRB_FILL_BS", "GRB_FILL_PSHIFT"):
