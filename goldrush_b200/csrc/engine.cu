@@ -205,7 +205,7 @@ struct grb_ctx
   DevBuf<GrbReadPlan> b_plan;
   DevBuf<uint64_t> b_tab_key, b_tab_mask;
   DevBuf<grb_decision> d_dec;
-  size_t query_smem = 0;
+  size_t query_smem = 0, query2_smem = 0;
   // batch engine (kernels_batch.cuh)
   bool batch_mode = true;
   uint32_t batch_reads = 128;  // reads per speculative batch
@@ -1076,7 +1076,7 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
       }
     }
     const char* bs_env = getenv("GRB_FILL_BS");
-    const bool bs512 = bs_env && strcmp(bs_env, "512") == 0;
+    const bool bs512 = !(bs_env && strcmp(bs_env, "1024") == 0); // measured faster on B200 (60 vs 65 ms)
     uint64_t part_limit = 1024;
     if (const char* e = getenv("GRB_FILL_MAXPART")) {
       const long v = strtol(e, nullptr, 10);
@@ -1115,7 +1115,7 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
       const double share = std::min(1.0, (double)(1ull << pshift) / (double)c->filt.bits);
       uint64_t cap = std::min<uint64_t>((scratch_mb << 20) / 4 / n_part,
                                         (uint64_t)((double)max_probes * share * 1.05) + 65536 + 4096);
-      cap = std::min<uint64_t>(std::max<uint64_t>(cap, 131072), 0xFFFFF000u);
+      cap = std::min<uint64_t>(std::max<uint64_t>(cap, 131072), 0xFFFFF000ull / n_part); // 32-bit list index
       const uint64_t round_probes =
         std::max<uint64_t>((uint64_t)((double)(cap - 65536) / 1.05 / share), GRB_FILL_CHUNK * h);
       const uint64_t round_chunks = std::max<uint64_t>(1, round_probes / (GRB_FILL_CHUNK * h));
@@ -1129,9 +1129,9 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
       GRB_CUDA(c, c->fill_cursor.reserve(n_part + 1, 0, s));
       GrbFillPart fp{ c->fill_lists.p, c->fill_cursor.p, n_part, pshift, (uint32_t)cap, 0 };
       const size_t dyn = (size_t)c->gt_groups * 256 * 32 +
-                         ((size_t)(bs512 ? 1024 : GRB_FILL_CHUNK) * h + 3 * (size_t)n_part + 1) * 4;
+                         ((size_t)(bs512 ? 1024 : GRB_FILL_CHUNK) * h * 2 + 3 * (size_t)n_part + 1) * 4;
       const int smem_optin = (int)((size_t)GRB_MAX_GROUPS * 256 * 32 +
-                                   ((size_t)GRB_FILL_CHUNK * GRB_PART_H + 3 * 1024 + 1) * 4);
+                                   ((size_t)GRB_FILL_CHUNK * GRB_PART_H * 2 + 3 * 1024 + 1) * 4);
       if (!c->fill_attr) {
         GRB_CUDA(c, cudaFuncSetAttribute(k_fill_part<1024, 2048, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          smem_optin));
@@ -1139,7 +1139,8 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
                                          smem_optin));
         c->fill_attr = true;
       }
-      // one 1024-thread CTA per SM at 64 registers, or (GRB_FILL_BS=512) one 512-thread CTA at 106
+      // two 512-thread CTAs per SM over 1024-position sub-chunks (default), or GRB_FILL_BS=1024:
+      // one 1024-thread CTA over the whole chunk
       c->kbegin();
       uint64_t n_launch = 0;
       for (uint64_t c0 = 0; c0 < chunk_read.size(); c0 += round_chunks) {
@@ -1846,8 +1847,13 @@ batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
                                      (int)c->b2_smem_max));
     GRB_CUDA(c, cudaFuncSetAttribute(k2_cmat<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)c->b2_smem_max));
+    c->query2_smem = (size_t)c->gt_groups * 256 * 32 + (size_t)c->prm.sw_words * 8 +
+                     (size_t)c->prm.table_size * 8;
+    if (c->query2_smem > c->b2_smem_max) {
+      return c->fail(GRB_ERR_ARG, "tile_length x hash_num too large for the shared-memory vote table");
+    }
     GRB_CUDA(c, cudaFuncSetAttribute(k2_query<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)c->query_smem));
+                                     (int)c->query2_smem));
     c->b2_attr = true;
   }
   return GRB_OK;
@@ -1924,8 +1930,8 @@ launch_batch2(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
   c->launches += 1;
   c->kbegin();
-  k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
-    c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state, 0u, b.n_bt);
+  k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query2_smem, s>>>(
+    c->reads_dev(), c->d_seed, c->d_gtab, c->gt_groups, c->filt, c->prm, bd, b2, c->d_state, 0u, b.n_bt);
   c->kend(GRB_K_QUERY);
   c->kbegin();
   k2_cmat<256><<<b.nb, 256, cmat_smem, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state, n_cap, us,
@@ -2107,8 +2113,9 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   c->launches += 1;
   if (!c->comm) {
     c->kbegin();
-    k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
-      c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state, 0u, b.n_bt);
+    k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query2_smem, s>>>(
+      c->reads_dev(), c->d_seed, c->d_gtab, c->gt_groups, c->filt, c->prm, bd, b2, c->d_state, 0u,
+      b.n_bt);
     c->kend(GRB_K_QUERY);
   } else {
     // W GPUs: this rank's share of the batch's tiles, then one NCCL group gathers every per-tile
@@ -2117,9 +2124,9 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
     const GrbShare sh = grb_share(b.n_bt, g.rank, g.world);
     c->kbegin();
     if (sh.hi > sh.lo) {
-      k2_query<512><<<grid_for(sh.hi - sh.lo, 1, 1u << 20), 512, c->query_smem, s>>>(
-        c->reads_dev(), c->d_seed, c->filt, c->prm, bd, b2, c->d_state, (uint32_t)sh.lo,
-        (uint32_t)sh.hi);
+      k2_query<512><<<grid_for(sh.hi - sh.lo, 1, 1u << 20), 512, c->query2_smem, s>>>(
+        c->reads_dev(), c->d_seed, c->d_gtab, c->gt_groups, c->filt, c->prm, bd, b2, c->d_state,
+        (uint32_t)sh.lo, (uint32_t)sh.hi);
     }
     c->kend(GRB_K_QUERY, sh.hi > sh.lo ? 1 : 0);
     c->kbegin();

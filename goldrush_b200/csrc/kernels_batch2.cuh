@@ -116,16 +116,23 @@ grb2_vote_add(uint32_t* vk, uint32_t* vc, uint32_t mask, uint32_t id, uint32_t d
 }
 
 // One CTA per batch tile (grid-strided).  Dynamic shared memory:
-//   GrbSeedTables | uint64 sw[sw_words] | uint32 keys[table_size] | uint32 counts[table_size]
+//   ulonglong2 gL[ng * 256] | gR[ng * 256] | uint64 sw[sw_words] | uint32 keys[table_size] |
+//   uint32 counts[table_size]
+// Hashing goes through the grouped half-hash tables (nthash.cuh): ceil(half / 4) 16-byte reads per
+// half hash instead of one read and one base extraction per care position, which brings the kernel
+// under 64 registers so that two CTAs share an SM and one CTA's table set-up / write-out overlaps
+// the other's probes.
 template<int BS>
-__global__ void __launch_bounds__(BS)
-k2_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilterDev filt,
+__global__ void __launch_bounds__(BS, 2)
+k2_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g,
+         const ulonglong2* __restrict__ gtab, uint32_t ng, GrbFilterDev filt,
          GrbSelParams prm, GrbBatchDev bd, GrbB2 b2, const GrbSelState* __restrict__ state,
          uint32_t bt_lo, uint32_t bt_hi)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GrbSeedTables& st = *reinterpret_cast<GrbSeedTables*>(smem_raw);
-  uint64_t* sw = reinterpret_cast<uint64_t*>(smem_raw + sizeof(GrbSeedTables));
+  ulonglong2* gL = reinterpret_cast<ulonglong2*>(smem_raw);
+  ulonglong2* gR = gL + ng * 256;
+  uint64_t* sw = reinterpret_cast<uint64_t*>(gR + ng * 256);
   uint32_t* keys = reinterpret_cast<uint32_t*>(sw + prm.sw_words);
   uint32_t* counts = keys + prm.table_size;
   __shared__ uint32_t s_hits, s_miss;
@@ -134,10 +141,10 @@ k2_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilter
   if (state->halt) {
     return;
   }
-  for (unsigned i = threadIdx.x; i < sizeof(GrbSeedTables) / 8; i += BS) {
-    reinterpret_cast<uint64_t*>(&st)[i] = reinterpret_cast<const uint64_t*>(seeds_g)[i];
+  for (unsigned i = threadIdx.x; i < 2 * ng * 256; i += BS) {
+    gL[i] = gtab[i];
   }
-  const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
+  const uint32_t T = prm.tile_len, k = prm.k, h = prm.h, half = seeds_g->half;
   const uint32_t tmask = prm.table_size - 1;
 
   // tiles [bt_lo, bt_hi) of the batch: the whole batch on one GPU, this rank's share on several
@@ -172,14 +179,21 @@ k2_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilter
     for (uint32_t f = threadIdx.x; f < frames; f += BS) {
       uint64_t rank[GRB_MAX_PATTERNS];
       bool all = true;
+      ulonglong2 lh = make_ulonglong2(0, 0); // left halves { fl, rl } at position p_left
+      uint32_t p_left = 0xFFFFFFFFu;
 #pragma unroll
       for (unsigned i = 0; i < GRB_MAX_PATTERNS; ++i) {
         if (i < h) {
           const uint32_t n_i = tl - (k + i) + 1; // valid positions of pattern i in this tile
           const uint32_t p = f < n_i ? f : n_i - 1; // stale tail keeps the last value
-          const GrbWindow w =
-            grb_window([&](uint64_t wi) { return sw[wi]; }, (uint64_t)(p0 & 31) + p);
-          const uint64_t hv = grb_hash_direct(st, i, w);
+          const uint64_t at = (uint64_t)(p0 & 31) + p;
+          if (p != p_left) {
+            lh = grb_group_half(gL, ng, grb_lo64([&](uint64_t wi) { return sw[wi]; }, at));
+            p_left = p;
+          }
+          const ulonglong2 rh =
+            grb_group_half(gR, ng, grb_lo64([&](uint64_t wi) { return sw[wi]; }, at + half + i));
+          const uint64_t hv = grb_combine(i, lh.x, lh.y, rh.x, rh.y);
           bool bit;
           grb_probe_block(filt, grb_fastmod(hv, filt.bits, filt.inv), bit, rank[i]);
           all &= bit;

@@ -121,7 +121,7 @@ grb_set_bit_pos(const GrbFilterDev& f, uint64_t pos)
 }
 
 // Dynamic shared memory: ulonglong2 gL[ng * 256] | gR[ng * 256] | uint32 stage[SUB * h] |
-// hist[n_part] | sbase[n_part + 1] | gbase[n_part]
+// sdst[SUB * h] | hist[n_part] | sbase[n_part + 1] | gbase[n_part]
 // A CTA walks its 2048-position chunk in sub-chunks of SUB positions (BS threads, SUB / BS
 // positions per thread), so that two or three CTAs fit on an SM and overlap each other's barriers.
 template<int BS, int SUB, int MINB>
@@ -146,7 +146,8 @@ k_fill_part(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g,
   const unsigned half = seeds_g->half, k = seeds_g->k, h = seeds_g->h;
   const uint32_t P = fp.n_part;
   uint32_t* stage = reinterpret_cast<uint32_t*>(gR + ng * 256);
-  uint32_t* hist = stage + SUB * h;
+  uint32_t* sdst = stage + SUB * h;
+  uint32_t* hist = sdst + SUB * h;
   uint32_t* sbase = hist + P;
   uint32_t* gbase = sbase + P + 1;
   const uint32_t omask = (1u << fp.pshift) - 1u;
@@ -232,33 +233,33 @@ k_fill_part(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g,
       }
     }
     __syncthreads();
+    // scatter into the staging area, bucket by bucket, together with each entry's destination in
+    // the partition lists (so that the copy-out below is a plain coalesced loop); entries past a
+    // list's capacity take the direct atomicOr instead
 #pragma unroll
     for (int it = 0; it < PER; ++it) {
 #pragma unroll
       for (int i = 0; i < GRB_PART_H; ++i) {
         if (plr[it][i] != 0xFFFFFFFFu) {
-          stage[sbase[plr[it][i] >> 16] + (plr[it][i] & 0xFFFFu)] = off[it][i];
+          const uint32_t p = plr[it][i] >> 16, lr = plr[it][i] & 0xFFFFu;
+          const uint32_t g = gbase[p] + lr;
+          const uint32_t at = sbase[p] + lr;
+          if (g < fp.cap) {
+            stage[at] = off[it][i];
+            sdst[at] = p * fp.cap + g;
+          } else {
+            sdst[at] = 0xFFFFFFFFu;
+            grb_set_bit_pos(filt, ((uint64_t)p << fp.pshift) | off[it][i]);
+          }
         }
       }
     }
     __syncthreads();
     const uint32_t total = s_total;
     for (uint32_t idx = threadIdx.x; idx < total; idx += BS) {
-      uint32_t lo = 0, hi = P; // last p with sbase[p] <= idx
-      while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (sbase[mid] <= idx) {
-          lo = mid;
-        } else {
-          hi = mid;
-        }
-      }
-      const uint32_t g = gbase[lo] + (idx - sbase[lo]);
-      const uint32_t o = stage[idx];
-      if (g < fp.cap) {
-        fp.lists[(uint64_t)lo * fp.cap + g] = o;
-      } else {
-        grb_set_bit_pos(filt, ((uint64_t)lo << fp.pshift) | o);
+      const uint32_t d = sdst[idx];
+      if (d != 0xFFFFFFFFu) {
+        fp.lists[d] = stage[idx];
       }
     }
   }

@@ -125,7 +125,7 @@ def test_bitvector_and_rank_match_oracle(h, bits):
 
 @pytest.mark.parametrize("h,bits,env", [
     (3, 1000000 + 64, {"GRB_FILL_PSHIFT": "16"}),                       # 16 partitions
-    (3, 1000000 + 64, {"GRB_FILL_PSHIFT": "16", "GRB_FILL_BS": "512"}),
+    (3, 1000000 + 64, {"GRB_FILL_PSHIFT": "16", "GRB_FILL_BS": "1024"}),
     (1, 333376, {"GRB_FILL_PSHIFT": "12"}),                             # 82 partitions
     (4, 5000000 + 128, {"GRB_FILL_PSHIFT": "14"}),                      # 306 partitions
     (4, 5000000 + 128, {"GRB_FILL_PSHIFT": "12", "GRB_FILL_MAXPART": "100"}),  # folded to 77

@@ -42,8 +42,8 @@ def main():
     variants = {"direct": {"GRB_FILL": "direct"}}
     for ps in (23, 24, 25, 26, 27):
         variants[f"part_pshift{ps}"] = {"GRB_FILL": "part", "GRB_FILL_PSHIFT": str(ps)}
-        variants[f"part_pshift{ps}_bs512"] = {"GRB_FILL": "part", "GRB_FILL_PSHIFT": str(ps),
-                                             "GRB_FILL_BS": "512"}
+        variants[f"part_pshift{ps}_bs1024"] = {"GRB_FILL": "part", "GRB_FILL_PSHIFT": str(ps),
+                                              "GRB_FILL_BS": "1024"}
     only = os.environ.get("FILL_AB_ONLY")
     if only:
         variants = {k: v for k, v in variants.items() if k in only.split(",")}
