@@ -217,6 +217,10 @@ def bench_ours(args, w):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the one JSON line must be the only thing on stdout: NCCL prints its version banner there
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -336,7 +340,9 @@ def bench_ours(args, w):
         with open(os.path.join(ROOT, "profiles", "roofline_inputs.json")) as f:
             ri = json.load(f)
         sector_peak = float(ri["random_sector_gather_gbs"])
-        traffic = ri["k2_query_dram_bytes_per_launch"] if args.workload == "cfg2" else None
+        # measured DRAM bytes per probe of the committed capture x the probes of one launch here
+        traffic = (ri["k2_query_dram_bytes_per_probe"] * probes_per_step * args.steps / max(1, q_n)
+                   if args.workload == "cfg2" else None)
     except (OSError, KeyError, ValueError):
         pass
     roofline = {"bound": "hbm", "kernel": "k2_query", "achieved": achieved, "peak": peak,
@@ -382,7 +388,7 @@ def bench_ours(args, w):
 
     if rank == 0:
         cpu = None
-        if world == 1:
+        if world == 1 and not os.environ.get("GRB_BENCH_SKIP_CPU"):  # A/B runs skip the CPU leg
             cores = os.cpu_count() or 1
             path, n = write_sample(grb, w, REF_SAMPLE_READS)
             try:
@@ -415,6 +421,8 @@ def bench_ours(args, w):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         grb.api.comm_destroy()

@@ -208,7 +208,7 @@ struct grb_ctx
   size_t query_smem = 0, query2_smem = 0;
   // batch engine (kernels_batch.cuh)
   bool batch_mode = true;
-  uint32_t batch_reads = 128;  // reads per speculative batch
+  uint32_t batch_reads = 320;  // reads per speculative batch (A/B on B200: 64..800, profiles/README.md)
   uint32_t batch_tiles = 8192; // tile budget per batch (a single longer read still forms a batch)
   uint32_t dirty_bits_log2 = 28;
   uint64_t bt_cap = 0;         // capacity of the per-batch buffers, in tiles
@@ -256,6 +256,8 @@ struct grb_ctx
   // ---- multi-GPU (comm.cuh): the process-wide NCCL communicator, when this context's device is
   // the one it was created on and it spans more than one rank ----
   GrbComm* comm = nullptr;
+  bool shard_query = false;  // pass-2 query sharding (GRB_SHARD_QUERY=1): see DESIGN.md 6 for why
+                             // it is off by default (the exchange costs more than the query saves)
   DevBuf<uint64_t> comm_tmp; // all-gather landing zone of the pass-1 OR-reduce
   int fail_nccl(ncclResult_t r, const char* what)
   {
@@ -534,6 +536,12 @@ grb_create(const grb_params* p, grb_ctx** out)
     c->batch_mode = strcmp(e, "serial") != 0;
     c->batch_ver = strcmp(e, "batch1") == 0 ? 1 : (strcmp(e, "batch2") == 0 ? 2 : 3);
   }
+  if (const char* e = getenv("GRB_BATCH_TILES")) { // tile budget of a batch (26-bit probe index caps it)
+    const long v = strtol(e, nullptr, 10);
+    if (v > 0 && v <= (1 << 20)) {
+      c->batch_tiles = (uint32_t)v;
+    }
+  }
   if (const char* e = getenv("GRB_BATCH_READS")) {
     const long v = strtol(e, nullptr, 10);
     if (v > 0 && v <= 65536) {
@@ -546,6 +554,8 @@ grb_create(const grb_params* p, grb_ctx** out)
     const char* off = getenv("GRB_COMM");
     if (g.comm && g.world > 1 && g.device == c->device && !(off && strcmp(off, "0") == 0)) {
       c->comm = &g;
+      const char* sq = getenv("GRB_SHARD_QUERY");
+      c->shard_query = sq && strcmp(sq, "1") == 0;
     }
   }
   if ((e = grb_pool_alloc((void**)&c->d_seed, sizeof(GrbSeedTables))) != cudaSuccess ||
@@ -1494,7 +1504,16 @@ sel_prepare(grb_ctx* c, uint64_t max_len)
     q.k = (uint32_t)k;
     q.h = (uint32_t)h;
     q.cand_cap = (uint32_t)(T * h / 3 + 1);
+    // A tile votes for at most T * h distinct ids.  The v3 engine never adds to the per-tile tables
+    // after the query (its commit keeps deltas apart), so it needs no slack beyond a load factor
+    // below 3/4; the older engines re-vote into the tables and keep the 2x sizing.
     q.table_size = (uint32_t)next_pow2(2 * T * h);
+    if (c->batch_mode && c->batch_ver == 3) {
+      const char* e = getenv("GRB_VOTE_TABLE");
+      if (!(e && strcmp(e, "wide") == 0)) {
+        q.table_size = (uint32_t)next_pow2(T * h + T * h / 3 + 1);
+      }
+    }
     q.sw_words = (uint32_t)((T + k + 63) / 32 + 4);
     q.silver = c->p.silver_path;
     q.threshold = c->p.threshold;
@@ -2111,7 +2130,7 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   GRB_CUDA(c, cudaMemsetAsync(b3.barrier, 0, 8, s));
   k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
   c->launches += 1;
-  if (!c->comm) {
+  if (!c->comm || !c->shard_query) {
     c->kbegin();
     k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query2_smem, s>>>(
       c->reads_dev(), c->d_seed, c->d_gtab, c->gt_groups, c->filt, c->prm, bd, b2, c->d_state, 0u,
@@ -2278,7 +2297,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       if (!bp.batches.empty()) {
         bp.tile_first.push_back(bp.batches.back().n_bt);
         // with W ranks every per-tile buffer holds W equal shares (the last one padded)
-        const uint64_t pad_bt = c->comm ? (uint64_t)c->comm->world : 0;
+        const uint64_t pad_bt = (c->comm && c->shard_query) ? (uint64_t)c->comm->world : 0;
         rc = c->batch_ver == 3
                ? batch3_prepare(c, std::max<uint64_t>(max_bt, 1) + pad_bt, max_len / T, max_cm, max_nb)
                : c->batch_ver == 2

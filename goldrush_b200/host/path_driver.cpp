@@ -18,6 +18,7 @@
 #include <string>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <future>
 #include <thread>
 #include <unistd.h>
 #include <unordered_set>
@@ -272,9 +273,22 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
     }
   }
 
+  // host threads for the bookkeeping loops: -j if given, else the machine's cores divided by the
+  // ranks sharing it (one process per GPU).  Set explicitly on every region: launchers such as
+  // torchrun export OMP_NUM_THREADS=1.
+  int n_threads = o->jobs > 0 ? o->jobs : (int)std::max(1u, std::thread::hardware_concurrency());
+  {
+    int c_rank = 0, c_world = 1;
+    grb_comm_info(ctx, &c_rank, &c_world);
+    if (o->jobs <= 0 && c_world > 1) {
+      n_threads = std::max(1, n_threads / c_world);
+    }
+  }
+  n_threads = std::min(n_threads, 64);
+
   // ---- per-read Phred statistics from the device sums ----
   std::vector<uint32_t> avg(nreads), delta(nreads);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) num_threads(n_threads)
   for (int64_t i = 0; i < (int64_t)nreads; ++i) {
     grb_phred_finalize(meta[i].phred_first_half_sum, meta[i].phred_total_sum, meta[i].qual_len,
                        &avg[i], &delta[i]);
@@ -416,23 +430,15 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
   mark("pass1+rank");
   // ---- pass 2 ----
   log("assigning tiles\n");
+  // Pass 2 runs in slices of reads (grb_select_reads keeps its loop state between calls); while the
+  // GPU works on slice i + 1 a host task turns slice i's decisions into output records, so the
+  // writers (goldrush_path.cpp:973-976,996-1002,1055-1070,1174-1179,182-184) cost no wall time.
   std::vector<grb_decision> dec(nreads);
   std::vector<grb_path_stats> snaps(p.max_paths + 2);
   uint32_t n_snaps = 0;
   int finished = 0;
-  if (nreads && (rc = grb_select_reads(ctx, 0, nreads, dec.data(), snaps.data(),
-                                       (uint32_t)snaps.size(), &n_snaps, &finished)) != GRB_OK) {
-    return fail(rc);
-  }
-  R.ms_pass2 = grb_last_device_ms(ctx);
-  grb_path_stats cur{};
-  uint64_t curr_path = 1;
-  if ((rc = grb_select_state(ctx, &cur, &curr_path, nullptr)) != GRB_OK) {
-    return fail(rc);
-  }
 
-  mark("pass2");
-  // ---- outputs (goldrush_path.cpp:973-976,996-1002,1055-1070,1174-1179,182-184) ----
+  // ---- output stage state (touched only by the emit task, one slice at a time, in order) ----
   // Pass A (serial, O(#reads)): which records go where.  Pass B (parallel over records, chunked):
   // assemble the record bytes.  Pass C (serial, in record order): write, digest, path log lines.
   double tab[256];
@@ -452,11 +458,29 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
   std::vector<Rec> recs;
   const uint64_t T = p.tile_length;
   uint64_t visited_reads = 0;
-  {
-    uint32_t snap_i = 0;
-    for (uint64_t i = 0; i < nreads; ++i) {
+  bool past_end = false; // a GRB_NOT_VISITED read was seen: nothing after it was reached
+  uint32_t snap_a = 0;   // pass A's cursor into snaps
+  Fnv digest;
+  OutFile out;
+  out.write = o->write_outputs != 0;
+  out.digest = &digest;
+  const std::string prefix = o->prefix ? o->prefix : "goldrush_out";
+  out.open(p.silver_path ? prefix + "_1.fq" : prefix + ".fa");
+  const char first_char = p.silver_path ? '@' : '>';
+  uint32_t path_now = 1, snap_i = 0;
+  double phred_sum = 0;
+  const bool want_phred = !o->quiet && o->verbose;
+  const bool want_bytes = out.write;
+  std::vector<char> buf;
+  const size_t kChunkBytes = (size_t)512 << 20;
+
+  // snaps_seen = snapshots known when the slice was handed over (the array itself is shared)
+  auto emit = [&](uint64_t first, uint64_t count, uint32_t snaps_seen) {
+    recs.clear();
+    for (uint64_t i = first; i < first + count && !past_end; ++i) {
       const grb_decision& d = dec[i];
       if (d.verdict == GRB_NOT_VISITED) {
+        past_end = true;
         break;
       }
       ++visited_reads;
@@ -486,120 +510,146 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
       r.id_len = l;
       r.bytes = 1 + l + (r.trimmed ? 9 : 11) + r.sl + 1 + (p.silver_path ? 2 + r.ql + 1 : 0);
       // silver_path_check (goldrush_path.cpp:156-187): a snapshot was taken right after this read
-      r.closes_path = snap_i < n_snaps && snaps[snap_i].rollover_read == i;
+      r.closes_path = snap_a < snaps_seen && snaps[snap_a].rollover_read == i;
       if (r.closes_path) {
-        ++snap_i;
+        ++snap_a;
       }
       recs.push_back(r);
       ++R.reads_selected;
       R.bases_selected += r.sl;
     }
-  }
-  Fnv digest;
-  OutFile out;
-  out.write = o->write_outputs != 0;
-  out.digest = &digest;
-  const std::string prefix = o->prefix ? o->prefix : "goldrush_out";
-  out.open(p.silver_path ? prefix + "_1.fq" : prefix + ".fa");
-  const char first_char = p.silver_path ? '@' : '>';
-  uint32_t path_now = 1, snap_i = 0;
-  double phred_sum = 0;
-  const bool want_phred = !o->quiet && o->verbose;
-  const bool want_bytes = out.write;
-  int n_threads = o->jobs > 0 ? o->jobs : (int)std::max(1u, std::thread::hardware_concurrency());
-  n_threads = std::min(n_threads, 64);
-  std::vector<char> buf;
-  const size_t kChunkBytes = (size_t)512 << 20;
-  size_t r0 = 0;
-  while (r0 < recs.size()) {
-    size_t r1 = r0, bytes = 0;
-    while (r1 < recs.size() && (r1 == r0 || bytes + recs[r1].bytes <= kChunkBytes)) {
-      recs[r1].at = bytes;
-      bytes += recs[r1].bytes;
-      ++r1;
-    }
-    if (want_bytes && buf.size() < bytes) {
-      buf.resize(bytes);
-    }
+    size_t r0 = 0;
+    while (r0 < recs.size()) {
+      size_t r1 = r0, bytes = 0;
+      while (r1 < recs.size() && (r1 == r0 || bytes + recs[r1].bytes <= kChunkBytes)) {
+        recs[r1].at = bytes;
+        bytes += recs[r1].bytes;
+        ++r1;
+      }
+      if (want_bytes && buf.size() < bytes) {
+        buf.resize(bytes);
+      }
 #pragma omp parallel num_threads(n_threads)
-    {
-      std::vector<char> local; // record scratch when nothing is written (digest only)
+      {
+        std::vector<char> local; // record scratch when nothing is written (digest only)
 #pragma omp for schedule(dynamic, 4)
-      for (int64_t ri = (int64_t)r0; ri < (int64_t)r1; ++ri) {
-        Rec& r = recs[ri];
-        const grb_read_meta& m = meta[r.read];
-        char* dst;
-        if (want_bytes) {
-          dst = buf.data() + r.at;
-        } else {
-          if (local.size() < r.bytes) {
-            local.resize(r.bytes);
+        for (int64_t ri = (int64_t)r0; ri < (int64_t)r1; ++ri) {
+          Rec& r = recs[ri];
+          const grb_read_meta& m = meta[r.read];
+          char* dst;
+          if (want_bytes) {
+            dst = buf.data() + r.at;
+          } else {
+            if (local.size() < r.bytes) {
+              local.resize(r.bytes);
+            }
+            dst = local.data();
           }
-          dst = local.data();
-        }
-        char* w = dst;
-        *w++ = first_char;
-        memcpy(w, data + m.hdr_off, r.id_len);
-        w += r.id_len;
-        if (r.trimmed) {
-          memcpy(w, "_trimmed\n", 9);
-          w += 9;
-        } else {
-          memcpy(w, "_untrimmed\n", 11);
-          w += 11;
-        }
-        const char* sq = data + m.seq_off + r.s0;
-        for (size_t j = 0; j < r.sl; ++j) { // SeqReader folds the sequence to upper case
-          const unsigned char ch = (unsigned char)sq[j];
-          w[j] = (char)(ch - (((unsigned)(ch - 'a') < 26u) << 5));
-        }
-        w += r.sl;
-        *w++ = '\n';
-        const char* ql = data + m.qual_off + r.s0;
-        if (p.silver_path) {
-          *w++ = '+';
+          char* w = dst;
+          *w++ = first_char;
+          memcpy(w, data + m.hdr_off, r.id_len);
+          w += r.id_len;
+          if (r.trimmed) {
+            memcpy(w, "_trimmed\n", 9);
+            w += 9;
+          } else {
+            memcpy(w, "_untrimmed\n", 11);
+            w += 11;
+          }
+          const char* sq = data + m.seq_off + r.s0;
+          for (size_t j = 0; j < r.sl; ++j) { // SeqReader folds the sequence to upper case
+            const unsigned char ch = (unsigned char)sq[j];
+            w[j] = (char)(ch - (((unsigned)(ch - 'a') < 26u) << 5));
+          }
+          w += r.sl;
           *w++ = '\n';
-          memcpy(w, ql, r.ql);
-          w += r.ql;
-          *w++ = '\n';
-        }
-        Fnv hsh;
-        hsh.add(dst, r.bytes);
-        r.hash = hsh.h;
-        // the reference adds sum_phred of the written quality string (goldrush_path.cpp:1005-1008);
-        // for a whole read that is the running sum the device already holds
-        r.phred = 0;
-        if (want_phred) {
-          r.phred = (!r.trimmed && r.ql == m.qual_len) ? m.phred_total_sum : sum_phred_host(ql, r.ql, tab);
+          const char* ql = data + m.qual_off + r.s0;
+          if (p.silver_path) {
+            *w++ = '+';
+            *w++ = '\n';
+            memcpy(w, ql, r.ql);
+            w += r.ql;
+            *w++ = '\n';
+          }
+          Fnv hsh;
+          hsh.add(dst, r.bytes);
+          r.hash = hsh.h;
+          // the reference adds sum_phred of the written quality string (goldrush_path.cpp:1005-1008);
+          // for a whole read that is the running sum the device already holds
+          r.phred = 0;
+          if (want_phred) {
+            r.phred = (!r.trimmed && r.ql == m.qual_len) ? m.phred_total_sum : sum_phred_host(ql, r.ql, tab);
+          }
         }
       }
+      for (size_t ri = r0; ri < r1; ++ri) {
+        const Rec& r = recs[ri];
+        if (out.f) {
+          fwrite(buf.data() + r.at, 1, r.bytes, out.f);
+        }
+        digest.add((const char*)&r.hash, 8);
+        phred_sum += r.phred;
+        path_now = dec[r.read].path;
+        if (r.closes_path) {
+          if (o->verbose) {
+            log_path_stat(log, path_now, snaps[snap_i], phred_sum);
+          }
+          ++snap_i;
+          phred_sum = 0;
+          if (path_now + 1 <= p.max_paths) {
+            out.open(prefix + "_" + std::to_string(path_now + 1) + ".fq");
+          }
+        }
+      }
+      r0 = r1;
     }
-    for (size_t ri = r0; ri < r1; ++ri) {
-      const Rec& r = recs[ri];
-      if (out.f) {
-        fwrite(buf.data() + r.at, 1, r.bytes, out.f);
-      }
-      digest.add((const char*)&r.hash, 8);
-      phred_sum += r.phred;
-      path_now = dec[r.read].path;
-      if (r.closes_path) {
-        if (o->verbose) {
-          log_path_stat(log, path_now, snaps[snap_i], phred_sum);
-        }
-        ++snap_i;
-        phred_sum = 0;
-        if (path_now + 1 <= p.max_paths) {
-          out.open(prefix + "_" + std::to_string(path_now + 1) + ".fq");
-        }
-      }
-    }
-    r0 = r1;
+  };
+
+  uint64_t slice = 16384;
+  if (const char* e = getenv("GRB_SLICE_READS")) { // 0 = one call for the whole store
+    const long long v = atoll(e);
+    slice = v <= 0 ? nreads : (uint64_t)v;
   }
+  slice = std::max<uint64_t>(slice, 1);
+  std::future<void> pending;
+  int sel_rc = GRB_OK;
+  for (uint64_t first = 0; first < nreads; first += slice) {
+    const uint64_t count = std::min<uint64_t>(slice, nreads - first);
+    if (!finished) {
+      uint32_t got = 0;
+      sel_rc = grb_select_reads(ctx, first, count, dec.data() + first, snaps.data() + n_snaps,
+                                (uint32_t)snaps.size() - n_snaps, &got, &finished);
+      if (sel_rc != GRB_OK) {
+        break;
+      }
+      n_snaps += got;
+      R.ms_pass2 += grb_last_device_ms(ctx);
+    } // after exit(0) in the reference nothing else is visited: dec stays GRB_NOT_VISITED
+    if (pending.valid()) {
+      pending.get();
+    }
+    const uint32_t seen = n_snaps;
+    pending = std::async(std::launch::async, emit, first, count, seen);
+    if (finished) {
+      break; // the remaining reads were never reached
+    }
+  }
+  if (pending.valid()) {
+    pending.get();
+  }
+  if (sel_rc != GRB_OK) {
+    return fail(sel_rc);
+  }
+  grb_path_stats cur{};
+  uint64_t curr_path = 1;
+  if ((rc = grb_select_state(ctx, &cur, &curr_path, nullptr)) != GRB_OK) {
+    return fail(rc);
+  }
+  mark("pass2+outputs");
   for (uint64_t done = 10000; done <= visited_reads + 1; done += 10000) {
     log("processed %llu reads\n", (unsigned long long)done);
   }
   out.close();
-  mark("outputs");
   R.paths = (uint32_t)curr_path;
   if (!finished) {
     if (p.silver_path && p.max_paths > curr_path) { // goldrush_path.cpp:1257-1264

@@ -40,6 +40,7 @@ def main():
 
     def engine_run():
         with grb.Engine(seeds, **kw) as e:
+            e.profile_enable(True)
             e.reads_ingest_fastq(data)
             n = e.reads_count()
             e.reads_set_flags(np.full(n, 3, dtype=np.uint8))
@@ -55,12 +56,20 @@ def main():
 
     assert multi.init_comm(local) == (rank, world)
     assert grb.api.comm_info() == (rank, world)
-    bitsw, popw, decw, infow, _ = engine_run()
+    # default: pass 1 sharded + OR-reduced, pass 2 replicated
+    bitsw, popw, decw, infow, n_gather0 = engine_run()
     assert infow == (rank, world)
-    result["engine"] = {"bits_equal": bool(np.array_equal(bits1, bitsw)), "pop_equal": pop1 == popw,
-                        "dec_equal": bool(np.array_equal(dec1.view(np.uint8), decw.view(np.uint8))),
+    # GRB_SHARD_QUERY=1: each batch's speculative query sharded over tiles + all-gathered as well
+    os.environ["GRB_SHARD_QUERY"] = "1"
+    bitsq, popq, decq, _, n_gather1 = engine_run()
+    assert n_gather1 > n_gather0 >= 0
+    result["engine"] = {"bits_equal": bool(np.array_equal(bits1, bitsw) and np.array_equal(bits1, bitsq)),
+                        "pop_equal": pop1 == popw == popq,
+                        "dec_equal": bool(np.array_equal(dec1.view(np.uint8), decw.view(np.uint8)) and
+                                          np.array_equal(dec1.view(np.uint8), decq.view(np.uint8))),
                         "selected": int(((decw["verdict"] == 2) | (decw["verdict"] == 3)).sum())}
     multi.assert_replicas_agree(decw.view(np.uint8))
+    multi.assert_replicas_agree(decq.view(np.uint8))
 
     # ---- golden cases through the whole-stage call ----
     work = os.path.join(out_dir, f"rank{rank}")
@@ -80,7 +89,8 @@ def main():
             produced[case["name"]] = (outs, res)
         return produced[case["name"]][0]
 
-    for name in CASES:
+    for i, name in enumerate(CASES):
+        os.environ["GRB_SHARD_QUERY"] = "1" if i % 2 == 0 else "0"
         outs = outputs_for(pu.case_by_name(name), work)
         res = produced[name][1]
         result["cases"][name] = {"outputs": pu.digest_outputs(outs), "filter_bits": res.filter_bits,
