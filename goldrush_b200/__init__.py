@@ -20,6 +20,7 @@ from .api import (  # noqa: F401
     make_seed_pattern,
     phred_finalize,
     run_path,
+    run_two_stage,
     synth_fastq,
     synth_fastq_raw,
     free_host,

@@ -160,6 +160,8 @@ def lib():
         "grb_kernel_time": (i32, [vp, i32, P(dbl), P(u64)]),
         "grb_commit_profile": (i32, [vp, P(u64)]),
         "grb_run_path": (i32, [P(RunOptions), vp, sz, P(RunResult), C.c_char_p, sz]),
+        "grb_run_two_stage": (i32, [P(RunOptions), P(RunOptions), vp, sz, P(RunResult), P(RunResult),
+                                    C.c_char_p, sz]),
         "grb_synth_num_reads": (u64, [P(SynthParams)]),
         "grb_synth_fastq": (vp, [P(SynthParams), u64, u64, P(u64)]),
         "grb_free_host": (None, [vp]),
@@ -476,12 +478,8 @@ class Engine:
         return ms.value, n.value
 
 
-def run_path(fastq=None, input_path=None, prefix="goldrush_out", seed_preset="",
-             filter_file=None, ntcard=False, verbose=False, write_outputs=True, quiet=True,
-             device=0, nbytes=None, **params):
-    """grb_run_path: the whole GoldRush-Path stage (goldrush_path.cpp main()).
-    fastq: bytes, or a raw host address (int) with nbytes; None = read input_path."""
-    L = lib()
+def _run_options(input_path, prefix, seed_preset, filter_file, ntcard, verbose, write_outputs,
+                 quiet, device, params):
     o = RunOptions()
     o.params = default_params(**params)
     o.params.device = device
@@ -493,6 +491,17 @@ def run_path(fastq=None, input_path=None, prefix="goldrush_out", seed_preset="",
     o.verbose = int(verbose)
     o.write_outputs = int(write_outputs)
     o.quiet = int(quiet)
+    return o
+
+
+def run_path(fastq=None, input_path=None, prefix="goldrush_out", seed_preset="",
+             filter_file=None, ntcard=False, verbose=False, write_outputs=True, quiet=True,
+             device=0, nbytes=None, **params):
+    """grb_run_path: the whole GoldRush-Path stage (goldrush_path.cpp main()).
+    fastq: bytes, or a raw host address (int) with nbytes; None = read input_path."""
+    L = lib()
+    o = _run_options(input_path, prefix, seed_preset, filter_file, ntcard, verbose, write_outputs,
+                     quiet, device, params)
     res = RunResult()
     err = C.create_string_buffer(1024)
     if nbytes is None:
@@ -501,6 +510,32 @@ def run_path(fastq=None, input_path=None, prefix="goldrush_out", seed_preset="",
     if rc:
         raise GrbError(rc, err.value.decode())
     return res
+
+
+def run_two_stage(fastq, silver: dict, golden: dict, input_path=None, nbytes=None, device=0,
+                  write_outputs=True, quiet=True):
+    """grb_run_two_stage: the silver run and the golden run on its concatenated paths
+    (bin/goldrush:240-260) in one call.  `silver` / `golden` are run_path keyword dicts
+    (prefix, seed_preset, verbose and the opt:: parameters)."""
+    L = lib()
+
+    def opts(kw):
+        kw = dict(kw)
+        return _run_options(kw.pop("input_path", input_path), kw.pop("prefix", "goldrush_out"),
+                            kw.pop("seed_preset", ""), kw.pop("filter_file", None),
+                            kw.pop("ntcard", False), kw.pop("verbose", False),
+                            kw.pop("write_outputs", write_outputs), kw.pop("quiet", quiet), device, kw)
+
+    so, go = opts(silver), opts(golden)
+    rs, rg = RunResult(), RunResult()
+    err = C.create_string_buffer(1024)
+    if nbytes is None:
+        nbytes = len(fastq) if fastq is not None else 0
+    rc = L.grb_run_two_stage(C.byref(so), C.byref(go), fastq, nbytes, C.byref(rs), C.byref(rg), err,
+                             len(err))
+    if rc:
+        raise GrbError(rc, err.value.decode())
+    return rs, rg
 
 
 # ---- synthetic reads ------------------------------------------------------------------------------

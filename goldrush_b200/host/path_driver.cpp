@@ -129,9 +129,11 @@ log_path_stat(const Log& log, uint64_t curr_path, const grb_path_stats& s, doubl
 
 } // namespace
 
-extern "C" int
-grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_run_result* res,
-             char* err, size_t err_cap)
+// `capture` (may be NULL) receives the bytes of every output record, in output order: what `cat
+// <p>_1.fq ... <p>_M.fq` would give (bin/goldrush:249-251), for grb_run_two_stage.
+static int
+run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_run_result* res,
+              char* err, size_t err_cap, std::vector<char>* capture)
 {
   const double t_wall0 = now_ms();
   const bool timing = getenv("GRB_TIMING") != nullptr; // host-side phase clock on stderr
@@ -343,18 +345,29 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
       fclose(ff);
     }
   }
-  auto read_id = [&](uint64_t i) {
+  // ---- pass-1 filters (goldrush_path.cpp:261-301) ----
+  // The reference inserts the NAME of every read dropped here into filter_out_reads and pass 2
+  // skips every read whose name is in that set (:907-932), i.e. the dropped read itself and any
+  // other read carrying the same name.  Same rule, without 10^5 string inserts: the dropped names
+  // (and the -f names) are kept as sorted 64-bit hashes, a surviving read whose hash matches is
+  // confirmed by comparing the strings.
+  std::vector<uint8_t> flags(nreads, 0);
+  uint64_t by_len = 0, by_phred = 0, by_delta = 0, by_bases = 0, passed = 0;
+  auto id_span = [&](uint64_t i, const char** s0) {
     const char* hdr = data + meta[i].hdr_off;
     size_t l = 0;
     while (l < meta[i].hdr_len && hdr[l] != ' ' && hdr[l] != '\t') {
       ++l;
     }
-    return std::string(hdr, l);
+    *s0 = hdr;
+    return l;
   };
-
-  // ---- pass-1 filters (goldrush_path.cpp:261-301) ----
-  std::vector<uint8_t> flags(nreads, 0);
-  uint64_t by_len = 0, by_phred = 0, by_delta = 0, by_bases = 0, passed = 0;
+  auto hash_bytes = [](const char* s0, size_t l) {
+    Fnv f;
+    f.add(s0, l);
+    return f.h;
+  };
+  std::vector<uint8_t> dropped(nreads, 0);
   for (uint64_t i = 0; i < nreads; ++i) {
     if (meta[i].len < p.min_length) {
       ++by_len;
@@ -363,21 +376,69 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
     if (avg[i] < p.phred_min || delta[i] >= p.phred_delta) {
       by_phred += avg[i] < p.phred_min;
       by_delta += delta[i] >= p.phred_delta;
-      filter_out.insert(read_id(i));
+      dropped[i] = 1;
       continue;
     }
     if (meta[i].non_acgt) {
       ++by_bases;
-      filter_out.insert(read_id(i));
+      dropped[i] = 1;
       continue;
     }
     ++passed;
     R.bases_pass1 += meta[i].len;
     flags[i] = GRB_READ_PASS1;
   }
-  // pass-2 eligibility (goldrush_path.cpp:907-932): long enough and name not filtered out
+  std::vector<uint64_t> name_hash(nreads);
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+  for (int64_t i = 0; i < (int64_t)nreads; ++i) {
+    const char* s0;
+    const size_t l = id_span((uint64_t)i, &s0);
+    name_hash[i] = hash_bytes(s0, l);
+  }
+  struct Dropped
+  {
+    uint64_t hash;
+    int64_t read; // -1: a name of the -f list
+  };
+  std::vector<Dropped> drop_list;
   for (uint64_t i = 0; i < nreads; ++i) {
-    if (meta[i].len >= p.min_length && (filter_out.empty() || !filter_out.count(read_id(i)))) {
+    if (dropped[i]) {
+      drop_list.push_back(Dropped{ name_hash[i], (int64_t)i });
+    }
+  }
+  for (const std::string& nm : filter_out) {
+    drop_list.push_back(Dropped{ hash_bytes(nm.data(), nm.size()), -1 });
+  }
+  std::sort(drop_list.begin(), drop_list.end(),
+            [](const Dropped& x, const Dropped& y) { return x.hash < y.hash; });
+  auto name_is_dropped = [&](uint64_t i) {
+    auto it = std::lower_bound(drop_list.begin(), drop_list.end(), name_hash[i],
+                               [](const Dropped& x, uint64_t hsh) { return x.hash < hsh; });
+    if (it == drop_list.end() || it->hash != name_hash[i]) {
+      return false;
+    }
+    const char* s0;
+    const size_t l = id_span(i, &s0);
+    for (; it != drop_list.end() && it->hash == name_hash[i]; ++it) {
+      if (it->read < 0) {
+        if (filter_out.count(std::string(s0, l))) {
+          return true;
+        }
+        continue;
+      }
+      const char* t0;
+      const size_t tl = id_span((uint64_t)it->read, &t0);
+      if (tl == l && memcmp(s0, t0, l) == 0) {
+        return true;
+      }
+    }
+    return false;
+  };
+  // pass-2 eligibility (goldrush_path.cpp:907-932): long enough and name not filtered out
+#pragma omp parallel for schedule(static) num_threads(n_threads)
+  for (int64_t i = 0; i < (int64_t)nreads; ++i) {
+    if (meta[i].len >= p.min_length && !dropped[i] &&
+        (drop_list.empty() || !name_is_dropped((uint64_t)i))) {
       flags[i] |= GRB_READ_PASS2;
     }
   }
@@ -470,7 +531,7 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
   uint32_t path_now = 1, snap_i = 0;
   double phred_sum = 0;
   const bool want_phred = !o->quiet && o->verbose;
-  const bool want_bytes = out.write;
+  const bool want_bytes = out.write || capture != nullptr;
   std::vector<char> buf;
   const size_t kChunkBytes = (size_t)512 << 20;
 
@@ -587,6 +648,9 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
         if (out.f) {
           fwrite(buf.data() + r.at, 1, r.bytes, out.f);
         }
+        if (capture) {
+          capture->insert(capture->end(), buf.data() + r.at, buf.data() + r.at + r.bytes);
+        }
         digest.add((const char*)&r.hash, 8);
         phred_sum += r.phred;
         path_now = dec[r.read].path;
@@ -670,4 +734,39 @@ grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_
     *res = R;
   }
   return GRB_OK;
+}
+
+extern "C" int
+grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_run_result* res,
+             char* err, size_t err_cap)
+{
+  return run_path_impl(o, fastq, fastq_len, res, err, err_cap, nullptr);
+}
+
+// The two goldrush-path launches of one assembly (bin/goldrush:240-260) in one call: the silver
+// run, then the golden run on the concatenated silver paths, which stay in host memory instead of
+// travelling through <p>_N.fq files and a second process.  Both stages write exactly the files the
+// two separate runs write (when write_outputs is set).
+extern "C" int
+grb_run_two_stage(const grb_run_options* silver, const grb_run_options* golden, const char* fastq,
+                  size_t fastq_len, grb_run_result* res_silver, grb_run_result* res_golden,
+                  char* err, size_t err_cap)
+{
+  if (!silver || !golden || !silver->params.silver_path || golden->params.silver_path) {
+    return set_err(err, err_cap, "grb_run_two_stage: first stage must be --silver_path, second not",
+                   GRB_ERR_ARG);
+  }
+  std::vector<char> paths;
+  int rc = run_path_impl(silver, fastq, fastq_len, res_silver, err, err_cap, &paths);
+  if (rc != GRB_OK) {
+    return rc;
+  }
+  if (paths.empty()) { // the golden run would stop on an empty file (goldrush_path.cpp:247-250)
+    return set_err(err, err_cap, "grb_run_two_stage: the silver stage selected no read", GRB_ERR_FORMAT);
+  }
+  grb_run_options g = *golden;
+  if (!g.input_path) {
+    g.input_path = "(silver paths in memory)";
+  }
+  return run_path_impl(&g, paths.data(), paths.size(), res_golden, err, err_cap, nullptr);
 }

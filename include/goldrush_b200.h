@@ -304,6 +304,14 @@ typedef struct grb_run_result
 int grb_run_path(const grb_run_options* opt, const char* fastq, size_t fastq_len,
                  grb_run_result* result, char* err, size_t err_cap);
 
+/* Both goldrush-path launches of one assembly (bin/goldrush:240-260: the --silver_path run, `cat` of
+ * its <p>_N.fq files, the golden run on that file) in one call.  The silver paths go to the second
+ * stage through host memory; each stage still writes the files its own launch would write when
+ * its write_outputs is set, byte for byte.  silver->params.silver_path must be set, golden's not. */
+int grb_run_two_stage(const grb_run_options* silver, const grb_run_options* golden,
+                      const char* fastq, size_t fastq_len, grb_run_result* res_silver,
+                      grb_run_result* res_golden, char* err, size_t err_cap);
+
 /* ---- synthetic reads; host only, used by bench.py and the tests ---- */
 typedef struct grb_synth_params
 {

@@ -292,6 +292,29 @@ def test_cli_binary_matches_reference_fixture(name, workdir):
     assert pu.parse_stats(err) == g["stats"]
 
 
+def test_two_stage_call_equals_two_reference_runs(workdir):
+    """grb_run_two_stage (bin/goldrush:240-260 in one call): the silver files of `silver_default`
+    AND the golden path the reference wrote from their concatenation (`golden_default`), without
+    the files travelling through a second process."""
+    silver, golden = pu.case_by_name("silver_default"), pu.case_by_name("golden_default")
+    inp, extra = pu.make_input(silver, workdir, _product_outputs_for)
+    with open(inp, "rb") as f:
+        data = f.read()
+    ps, pg = os.path.join(workdir, "two.silver"), os.path.join(workdir, "two.golden")
+    for fn in os.listdir(workdir):
+        if fn.startswith("two."):
+            os.remove(os.path.join(workdir, fn))
+    rs, rg = grb.run_two_stage(data, dict(prefix=ps, **_args_to_params(silver["args"])),
+                               dict(prefix=pg, **_args_to_params(golden["args"])), input_path=inp)
+    s_outs = sorted((os.path.join(workdir, fn) for fn in os.listdir(workdir)
+                     if fn.startswith("two.silver")), key=lambda p: (len(p), p))
+    g_outs = [os.path.join(workdir, "two.golden.fa")]
+    assert pu.digest_outputs(s_outs) == GOLDEN["silver_default"]["outputs"]
+    assert pu.digest_outputs(g_outs) == GOLDEN["golden_default"]["outputs"]
+    assert rs.reads_selected > 0 and rg.reads_selected > 0
+    assert rg.num_reads == rs.reads_selected  # the second stage read exactly the silver records
+
+
 def test_cli_error_paths(workdir):
     import subprocess
     fa = os.path.join(workdir, "x.fa")
