@@ -421,3 +421,63 @@ def test_batch_engine_equals_serial_engine(shape):
         assert got[1] == ref[1], b
         assert got[2] == ref[2], b
         assert got[3] == ref[3] and got[4] == ref[4], b
+
+
+# ---- BASELINE.json sizes ---------------------------------------------------------------------------
+CFG2 = dict(genome=100_000_000, cov=30.0, read_len=25000, seed=1002)  # configs[1], SURVEY.md 8(d)
+CFG2_PARAMS = dict(kmer_size=22, weight=16, hash_num=3, tile_length=1000, block_size=10,
+                   unassigned_min=5, assigned_max=1, occupancy=0.1, threshold=10, phred_delta=5,
+                   ratio=0.9, max_paths=5, min_length=20000, silver_path=1, phred_min=20)
+
+
+def test_cfg2_shaped_sample_matches_cpu_oracle(workdir):
+    """Reads of the bench workload's shape (25 kbp, tile 1000, k 22 / w 16 / h 3, -P 20): the first
+    1500 reads of the cfg2 read set against the CPU oracle, byte for byte, with the genome size set
+    so that all five silver paths close inside the sample (rollovers + the exit(0) at path M + 1)."""
+    import subprocess
+    sp = grb.api.synth_params(CFG2["genome"], CFG2["cov"], CFG2["read_len"], CFG2["seed"])
+    data = grb.synth_fastq(sp, 0, 1500)
+    fq = os.path.join(workdir, "cfg2_sample.fq")
+    with open(fq, "wb") as f:
+        f.write(data)
+    params = dict(CFG2_PARAMS, genome_size=2_000_000)
+    res = grb.run_path(data, input_path=fq, prefix=os.path.join(workdir, "cfg2s.gpu"), quiet=True,
+                       seed_preset=SEED22, **params)
+    args = ["-k", "22", "-w", "16", "-s", SEED22, "-h", "3", "-t", "1000", "-b", "10", "-u", "5", "-a",
+            "1", "-o", "0.1", "-x", "10", "-d", "5", "-r", "0.9", "-M", "5", "-m", "20000", "-P", "20",
+            "-g", "2000000", "--silver_path"]
+    subprocess.check_call([pu.ORACLE] + args + ["-j", "8", "-i", fq, "-p",
+                                                os.path.join(workdir, "cfg2s.cpu")],
+                          stderr=subprocess.DEVNULL)
+    n_files = 0
+    for i in range(1, 6):
+        g, c = (os.path.join(workdir, f"cfg2s.{t}_{i}.fq") for t in ("gpu", "cpu"))
+        assert os.path.exists(g) == os.path.exists(c), i
+        if os.path.exists(c):
+            n_files += 1
+            with open(g, "rb") as fg, open(c, "rb") as fc:
+                assert pu.golden_cases.md5(fg.read()) == pu.golden_cases.md5(fc.read()), i
+    assert n_files >= 2 and res.paths >= 2 and res.reads_selected > 0
+
+
+def test_cfg2_full_size_is_independent_of_batching_and_fill_path(monkeypatch):
+    """The whole cfg2 read set (120 000 reads, 3.0 Gbp): how the work is cut must not show in the
+    result.  320-read batches + L2-partitioned fill + 16 384-read slices (defaults) against 96-read
+    batches + direct atomic fill + one slice: same output digest, same counts, same filter."""
+    sp = grb.api.synth_params(CFG2["genome"], CFG2["cov"], CFG2["read_len"], CFG2["seed"])
+    ptr, n = grb.synth_fastq_raw(sp)
+    try:
+        kw = dict(nbytes=n, input_path="(memory)", seed_preset=SEED22, write_outputs=False,
+                  quiet=True, genome_size=CFG2["genome"], **CFG2_PARAMS)
+        a = grb.run_path(ptr, **kw)
+        monkeypatch.setenv("GRB_BATCH_READS", "96")
+        monkeypatch.setenv("GRB_FILL", "direct")
+        monkeypatch.setenv("GRB_SLICE_READS", "0")
+        b = grb.run_path(ptr, **kw)
+    finally:
+        grb.free_host(ptr)
+    key = lambda r: (r.out_digest, r.num_reads, r.num_passed_reads, r.reads_visited, r.bases_pass2,
+                     r.reads_selected, r.bases_selected, r.filter_bits, r.pop, r.paths)
+    assert key(a) == key(b)
+    assert a.num_reads == 120000 and a.reads_selected > 20000 and a.paths in (5, 6)
+    assert a.pop < a.filter_bits and a.bases_pass2 == a.reads_visited * 25000
