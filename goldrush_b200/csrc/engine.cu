@@ -241,7 +241,7 @@ struct grb_ctx
   DevBuf<uint2> b2_rl;
   DevBuf<GrbReadPlan> b2_plan_out;
   // third generation (kernels_fix.cuh); shares the b2_* probe-index buffers
-  bool b3_attr = false;
+  bool b3_attr = false, b3_stage_attr = false;
   uint32_t b3_ctas = 0, b3_dcap = 0;
   uint64_t b3_cap_tiles = 0, b3_cmat_cap = 0;
   DevBuf<GrbShared3> b3_shared;
@@ -2181,16 +2181,25 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   c->kbegin();
   const unsigned g_small = (unsigned)c->sm_count * 8;
   const unsigned g_tiles = grid_for(b.n_bt, 1, (unsigned)c->sm_count * 8);
-  k3_mark<<<g_tiles, 256, 0, s>>>(c->reads_dev(), c->prm, bd, b3, c->d_state);
+  const size_t stage_smem = (size_t)T * h * 4;
+  if (2 * stage_smem > 48 * 1024 && !c->b3_stage_attr) {
+    GRB_CUDA(c, cudaFuncSetAttribute(k3_mark, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)stage_smem));
+    GRB_CUDA(c, cudaFuncSetAttribute(k3_members, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(2 * stage_smem)));
+    c->b3_stage_attr = true;
+  }
+  k3_mark<<<g_tiles, 256, stage_smem, s>>>(c->reads_dev(), c->prm, bd, b3, c->d_state);
   k3_set_clear<<<g_small, 256, 0, s>>>(b3, c->d_state);
   k3_dupset<<<g_small, 256, 0, s>>>(bd, b3, c->d_state);
-  k3_members<<<g_tiles, 256, 0, s>>>(c->reads_dev(), c->prm, bd, b3, c->d_state);
+  k3_members<<<g_tiles, 256, 2 * stage_smem, s>>>(c->reads_dev(), c->prm, bd, b3, c->d_state);
   k3_open<<<g_small, 256, 0, s>>>(c->filt, b3, c->d_state);
   k3_conf<<<g_small, 256, 0, s>>>(c->reads_dev(), c->prm, bd, b3, c->d_state);
   k3_seg<<<g_small, 256, 0, s>>>(b3, c->d_state);
   k3_scatter<<<g_small, 256, 0, s>>>(c->prm, bd, b3, c->d_state);
   k3_sort<<<g_small, 256, 0, s>>>(b3, c->d_state);
-  k3_frames<<<grid_for(b.nb, 1, g_small), 256, 0, s>>>(c->filt, c->prm, bd, b3, c->d_state);
+  k3_frames<<<grid_for((uint64_t)b.nb * GRB_FRAME_SPLIT, 1, g_small * 2), 256, 0, s>>>(
+    c->filt, c->prm, bd, b3, c->d_state);
   c->kend(GRB_K_DEDUPE, 10);
   {
     GrbReadsDev reads = c->reads_dev();

@@ -99,6 +99,7 @@ struct GrbB3
 //   k3_open     one shared entry per rank counted >= 2
 //   k3_conf     the listed probes of shared ranks become the conflict list (as before)
 // ---------------------------------------------------------------------------------------------
+#define GRB_FRAME_SPLIT 8 // CTAs sharing one read's conflict-frame list in k3_frames
 #define GRB_CTR_CONF 0   // conflicts
 #define GRB_CTR_SHARED 1 // shared ranks
 #define GRB_CTR_MEMBER 2 // member cursor
@@ -143,38 +144,48 @@ grb3_set_mask(uint32_t n_cand, uint32_t cap_mask)
   return (want - 1) & cap_mask;
 }
 
+// Dynamic shared memory: uint32 stage[T * h].  The candidates of a tile are collected in shared
+// memory and appended with one reservation per tile (the per-256-probe block append spent as long
+// in its two barriers as in the atomics: ncu, 21 barrier-stall cycles per issue).
 __global__ void __launch_bounds__(256)
 k3_mark(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
         const GrbSelState* __restrict__ state)
 {
+  extern __shared__ uint32_t k3_stage[];
   __shared__ uint32_t s_n, s_base;
   if (state->halt) {
     return;
   }
-  if (threadIdx.x == 0) {
-    s_n = 0;
-  }
-  __syncthreads();
   const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
   const uint32_t per_tile = T * h;
   for (uint32_t bt = blockIdx.x; bt < bd.n_bt; bt += gridDim.x) {
     const uint32_t b = bd.tile_read[bt];
     const uint32_t t = bt - bd.tile_first[b];
     const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, k);
-    for (uint32_t base = 0; base < per_tile; base += blockDim.x) {
-      const uint32_t rem = base + threadIdx.x;
-      bool take = false;
-      const uint32_t idx = bt * per_tile + rem;
-      if (rem < per_tile) {
-        const uint32_t f = rem / h, p = rem - f * h;
-        if (tl >= k + p && f < tl - (k + p) + 1) {
-          const uint64_t rank = __ldcs(&bd.stash[idx]) & ~GRB_STASH_NOFRAME;
-          const uint32_t bit = (uint32_t)(grb_mix64(rank) >> 20) & b3.bm_mask;
-          const uint32_t m = 1u << (bit & 31);
-          take = (atomicOr(&b3.bm[bit >> 5], m) & m) != 0;
+    if (threadIdx.x == 0) {
+      s_n = 0;
+    }
+    __syncthreads();
+    for (uint32_t rem = threadIdx.x; rem < per_tile; rem += blockDim.x) {
+      const uint32_t f = rem / h, p = rem - f * h;
+      if (tl >= k + p && f < tl - (k + p) + 1) {
+        const uint32_t idx = bt * per_tile + rem;
+        const uint64_t rank = __ldcs(&bd.stash[idx]) & ~GRB_STASH_NOFRAME;
+        const uint32_t bit = (uint32_t)(grb_mix64(rank) >> 20) & b3.bm_mask;
+        const uint32_t m = 1u << (bit & 31);
+        if (atomicOr(&b3.bm[bit >> 5], m) & m) {
+          k3_stage[atomicAdd(&s_n, 1u)] = idx;
         }
       }
-      grb3_block_append(take, idx, 0, b3.cand, nullptr, &b3.counters[GRB_CTR_CAND], &s_n, &s_base);
+    }
+    __syncthreads();
+    const uint32_t n = s_n;
+    if (threadIdx.x == 0 && n) {
+      s_base = atomicAdd(&b3.counters[GRB_CTR_CAND], n);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      b3.cand[s_base + i] = k3_stage[i];
     }
   }
 }
@@ -214,18 +225,16 @@ k3_dupset(GrbBatchDev bd, GrbB3 b3, const GrbSelState* __restrict__ state)
   }
 }
 
+// Dynamic shared memory: uint32 probe[T * h] | slot[T * h] (per-tile staging, as in k3_mark)
 __global__ void __launch_bounds__(256)
 k3_members(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
            const GrbSelState* __restrict__ state)
 {
+  extern __shared__ uint32_t k3_stage[];
   __shared__ uint32_t s_n, s_base;
   if (state->halt) {
     return;
   }
-  if (threadIdx.x == 0) {
-    s_n = 0;
-  }
-  __syncthreads();
   const uint32_t n_cand = b3.counters[GRB_CTR_CAND];
   if (n_cand == 0) {
     return;
@@ -233,38 +242,51 @@ k3_members(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
   const uint32_t mask = grb3_set_mask(n_cand, (uint32_t)b3.ix_mask);
   const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
   const uint32_t per_tile = T * h;
+  uint32_t* st_probe = k3_stage;
+  uint32_t* st_slot = k3_stage + per_tile;
   for (uint32_t bt = blockIdx.x; bt < bd.n_bt; bt += gridDim.x) {
     const uint32_t b = bd.tile_read[bt];
     const uint32_t t = bt - bd.tile_first[b];
     const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, k);
-    for (uint32_t base = 0; base < per_tile; base += blockDim.x) {
-      const uint32_t rem = base + threadIdx.x;
-      bool take = false;
-      uint32_t slot = 0;
-      const uint32_t idx = bt * per_tile + rem;
-      if (rem < per_tile) {
-        const uint32_t f = rem / h, p = rem - f * h;
-        if (tl >= k + p && f < tl - (k + p) + 1) {
-          const uint64_t rank = __ldcs(&bd.stash[idx]) & ~GRB_STASH_NOFRAME;
-          slot = (uint32_t)grb_mix64(rank) & mask;
-          while (true) {
-            const unsigned long long key = __ldcg(&b3.ix_tab[slot]);
-            if (key == rank) {
-              take = true;
-              break;
-            }
-            if (key == GRB_IX_EMPTY) {
-              break;
-            }
-            slot = (slot + 1) & mask;
+    if (threadIdx.x == 0) {
+      s_n = 0;
+    }
+    __syncthreads();
+    for (uint32_t rem = threadIdx.x; rem < per_tile; rem += blockDim.x) {
+      const uint32_t f = rem / h, p = rem - f * h;
+      if (tl >= k + p && f < tl - (k + p) + 1) {
+        const uint32_t idx = bt * per_tile + rem;
+        const uint64_t rank = __ldcs(&bd.stash[idx]) & ~GRB_STASH_NOFRAME;
+        uint32_t slot = (uint32_t)grb_mix64(rank) & mask;
+        bool take = false;
+        while (true) {
+          const unsigned long long key = __ldcg(&b3.ix_tab[slot]);
+          if (key == rank) {
+            take = true;
+            break;
           }
-          if (take) {
-            atomicAdd(&b3.ix_cnt[slot], 1u);
+          if (key == GRB_IX_EMPTY) {
+            break;
           }
+          slot = (slot + 1) & mask;
+        }
+        if (take) {
+          atomicAdd(&b3.ix_cnt[slot], 1u);
+          const uint32_t at = atomicAdd(&s_n, 1u);
+          st_probe[at] = idx;
+          st_slot[at] = slot;
         }
       }
-      grb3_block_append(take, idx, slot, b3.t_probe, b3.t_slot, &b3.counters[GRB_CTR_LISTED], &s_n,
-                        &s_base);
+    }
+    __syncthreads();
+    const uint32_t n = s_n;
+    if (threadIdx.x == 0 && n) {
+      s_base = atomicAdd(&b3.counters[GRB_CTR_LISTED], n);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      b3.t_probe[s_base + i] = st_probe[i];
+      b3.t_slot[s_base + i] = st_slot[i];
     }
   }
 }
@@ -445,11 +467,14 @@ k3_frames(GrbFilterDev filt, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
   }
   const uint32_t T = prm.tile_len, h = prm.h;
   const uint32_t stride = 2 + 2 * h;
-  for (uint32_t b = blockIdx.x; b < bd.nb; b += gridDim.x) {
+  // a read's frame list is shared by GRB_FRAME_SPLIT CTAs: one CTA per read left the GPU at 18 %
+  // of its warps on records that are random slot reads (ncu)
+  for (uint32_t u = blockIdx.x; u < bd.nb * GRB_FRAME_SPLIT; u += gridDim.x) {
+    const uint32_t b = u / GRB_FRAME_SPLIT, part = u - b * GRB_FRAME_SPLIT;
     const uint32_t nfr = b3.fl_n[b];
     const uint32_t bt0 = bd.tile_first[b];
     const uint64_t off = (uint64_t)bt0 * T;
-    for (uint32_t i = threadIdx.x; i < nfr; i += blockDim.x) {
+    for (uint32_t i = part * blockDim.x + threadIdx.x; i < nfr; i += blockDim.x * GRB_FRAME_SPLIT) {
       const uint32_t tf = b3.fl[off + i];
       const uint32_t t = tf >> 20, f = tf & 0xFFFFFu;
       const uint64_t* e = bd.stash + ((uint64_t)(bt0 + t) * T + f) * h;
