@@ -126,6 +126,7 @@ def lib():
         "grb_release_cached_memory": (None, []),
         "grb_reads_reserve": (i32, [vp, u64]),
         "grb_reads_ingest_fastq": (i32, [vp, vp, sz, i32, P(sz)]),
+        "grb_reads_readahead": (i32, [vp, vp, sz]),
         "grb_reads_count": (u64, [vp]),
         "grb_reads_get_meta": (i32, [vp, u64, u64, P(ReadMeta)]),
         "grb_reads_set_flags": (i32, [vp, u64, u64, vp]),
@@ -294,6 +295,10 @@ class Engine:
         n = len(data) if nbytes is None else nbytes
         self._chk(self._L.grb_reads_ingest_fastq(self._h, data, n, int(final), C.byref(used)))
         return used.value
+
+    def reads_readahead(self, base_ptr, total):
+        """Consecutive ingest calls will walk the host range [base_ptr, base_ptr + total)."""
+        self._chk(self._L.grb_reads_readahead(self._h, base_ptr, total))
 
     def reads_meta_array(self):
         """All read metadata as one numpy structured array (fields of grb_read_meta)."""

@@ -172,6 +172,15 @@ struct grb_ctx
   DevBuf<uint32_t> d_len;
   DevBuf<uint8_t> d_flags;
   bool flags_dirty = false;
+  // ingest read-ahead (grb_reads_readahead): the next chunk's bytes travel over PCIe on a second
+  // stream while the current chunk's decode kernels run
+  const char* ra_base = nullptr; // host range the caller will ingest chunk by chunk
+  size_t ra_total = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ra_ready = nullptr, ra_free = nullptr;
+  DevBuf<uint8_t> d_raw2;
+  const char* pf_host = nullptr; // host range now (being) copied into d_raw2
+  size_t pf_len = 0;
   // ingest scratch
   DevBuf<uint8_t> d_raw;
   DevBuf<uint32_t> d_blk_cnt;
@@ -597,6 +606,12 @@ grb_destroy(grb_ctx* c)
   if (c->stream) {
     cudaStreamSynchronize(c->stream);
   }
+  if (c->copy_stream) {
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamDestroy(c->copy_stream);
+    cudaEventDestroy(c->ra_ready);
+    cudaEventDestroy(c->ra_free);
+  }
   grb_pool_free(c->filt.blocks);
   grb_pool_free(c->filt.slots);
   grb_pool_free(c->d_state);
@@ -786,6 +801,19 @@ grb_reads_reserve(grb_ctx* c, uint64_t fastq_bytes)
 }
 
 int
+grb_reads_readahead(grb_ctx* c, const char* base, size_t total)
+{
+  cudaSetDevice(c->device);
+  if (c->copy_stream) {
+    GRB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  }
+  c->ra_base = base;
+  c->ra_total = base ? total : 0;
+  c->pf_host = nullptr;
+  return GRB_OK;
+}
+
+int
 grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_t* consumed)
 {
   cudaSetDevice(c->device);
@@ -805,7 +833,38 @@ grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_
   const uint64_t n_blk = padded / 4096;
   GRB_CUDA(c, c->d_raw.reserve(padded, 0, s));
   GRB_CUDA(c, cudaMemsetAsync(c->d_raw.p + (padded - 4096), 0, 4096, s));
-  GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, bytes, n, cudaMemcpyHostToDevice, s));
+  if (c->pf_host && bytes >= c->pf_host && bytes + n <= c->pf_host + c->pf_len) {
+    // the chunk was read ahead: a device-to-device copy re-aligns it to the start of d_raw
+    GRB_CUDA(c, cudaStreamWaitEvent(s, c->ra_ready, 0));
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, c->d_raw2.p + (bytes - c->pf_host), n,
+                                cudaMemcpyDeviceToDevice, s));
+  } else {
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, bytes, n, cudaMemcpyHostToDevice, s));
+  }
+  c->pf_host = nullptr;
+  if (c->ra_base && bytes >= c->ra_base && bytes + n < c->ra_base + c->ra_total) {
+    // start the next chunk's copy: it begins a little before this chunk's end because the caller
+    // re-sends the last partial record (records longer than the overlap fall back to a plain copy)
+    const size_t kOverlap = (size_t)16 << 20;
+    const char* lo = bytes + n - std::min(kOverlap, n);
+    const size_t len = std::min<size_t>((size_t)(c->ra_base + c->ra_total - lo), n + kOverlap);
+    if (!c->copy_stream) {
+      GRB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+      GRB_CUDA(c, cudaEventCreateWithFlags(&c->ra_ready, cudaEventDisableTiming));
+      GRB_CUDA(c, cudaEventCreateWithFlags(&c->ra_free, cudaEventDisableTiming));
+    }
+    if (len > c->d_raw2.cap) {
+      GRB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+      c->d_raw2.release();
+      GRB_CUDA(c, c->d_raw2.reserve(n + 2 * kOverlap, 0, s));
+    }
+    GRB_CUDA(c, cudaEventRecord(c->ra_free, s)); // d_raw2 is free once the copy above has run
+    GRB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ra_free, 0));
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_raw2.p, lo, len, cudaMemcpyHostToDevice, c->copy_stream));
+    GRB_CUDA(c, cudaEventRecord(c->ra_ready, c->copy_stream));
+    c->pf_host = lo;
+    c->pf_len = len;
+  }
   GRB_CUDA(c, c->d_blk_cnt.reserve(n_blk, 0, s));
   GRB_CUDA(c, c->d_blk_off.reserve(n_blk + 1, 0, s));
   k_nl_count<<<(unsigned)n_blk, 256, 0, s>>>(c->d_raw.p, c->d_blk_cnt.p);

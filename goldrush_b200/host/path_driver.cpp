@@ -231,6 +231,9 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     }
     const size_t kChunk = (size_t)1 << 30;
     size_t off = 0;
+    if ((rc = grb_reads_readahead(ctx, data, n)) != GRB_OK) { // next chunk's copy under this one's decode
+      return fail(rc);
+    }
     while (off < n) {
       const size_t len = std::min(kChunk, n - off);
       const int final = off + len == n;
@@ -247,6 +250,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
       }
       off += used;
     }
+    grb_reads_readahead(ctx, nullptr, 0);
   }
   mark("create+ingest");
   const uint64_t nreads = grb_reads_count(ctx);

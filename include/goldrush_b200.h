@@ -110,6 +110,11 @@ typedef struct grb_read_meta
  * *consumed = bytes used; re-send the tail with the next chunk (final != 0: a last record without
  * trailing newline is accepted).  bytes is HOST memory (pageable or pinned). */
 int grb_reads_ingest_fastq(grb_ctx* ctx, const char* bytes, size_t n, int final, size_t* consumed);
+/* Read-ahead hint: the following grb_reads_ingest_fastq calls take consecutive chunks of the HOST
+ * range [base, base + total) (a whole file, pinned for full effect).  While one chunk is decoded
+ * the next one's bytes are already copied on a second stream.  base = NULL switches it off; the
+ * range must stay valid until the last chunk has been ingested. */
+int grb_reads_readahead(grb_ctx* ctx, const char* base, size_t total);
 uint64_t grb_reads_count(const grb_ctx* ctx);
 int grb_reads_get_meta(grb_ctx* ctx, uint64_t first, uint64_t count, grb_read_meta* out);
 /* per-read flags decided by the host from grb_read_meta (length / Phred / delta / ACGT / -f list) */

@@ -92,6 +92,38 @@ def test_ingest_decodes_ragged_fastq():
             assert (m.phred_first_half_sum, m.phred_total_sum) == (f0, t0)
 
 
+def test_ingest_readahead_equals_plain_ingest():
+    """grb_reads_readahead: chunks copied ahead on the second stream (and re-aligned on the device)
+    decode to exactly the same read store as chunks copied inside the call."""
+    import ctypes
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, 3)
+    sp = grb.api.synth_params(150000, 20.0, 4000, 91)
+    data = grb.synth_fastq(sp)
+    buf = ctypes.create_string_buffer(data, len(data))
+    base = ctypes.addressof(buf)
+    chunk = 200003  # odd size: the device copy of a read-ahead chunk is never 16-byte aligned
+    out = []
+    for ahead in (False, True):
+        with grb.Engine(seeds, genome_size=150000, weight=16) as e:
+            if ahead:
+                e.reads_readahead(base, len(data))
+            off = 0
+            while off < len(data):
+                n = min(chunk, len(data) - off)
+                used = e.reads_ingest_fastq(base + off, final=(off + n == len(data)), nbytes=n)
+                assert used > 0
+                off += used
+            if ahead:
+                e.reads_readahead(None, 0)
+            meta = e.reads_meta_array()
+            n_reads = e.reads_count()
+            e.reads_set_flags(np.full(n_reads, 3, dtype=np.uint8))
+            e.filter_alloc(2000000 + 64)
+            e.build_bitvector()
+            out.append((n_reads, meta.tobytes(), e.copy_bitvector().tobytes()))
+    assert out[0][0] > 500 and out[0] == out[1]
+
+
 def _build_pair(rng, n_reads, lo, hi, seeds, bits, **params):
     """Engine + oracle filter holding the same reads / bit vector."""
     recs = _records(rng, n_reads, lo, hi)
