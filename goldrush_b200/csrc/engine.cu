@@ -141,6 +141,34 @@ grb_cached_memory_bytes(void)
   return P.idle_bytes;
 }
 
+// pinned + mapped upload arenas of destroyed contexts, kept for the next one (all of one size)
+static std::mutex g_arena_mu;
+static std::vector<void*> g_arena_idle;
+static void*
+grb_arena_take(size_t cap)
+{
+  {
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    if (!g_arena_idle.empty()) {
+      void* p = g_arena_idle.back();
+      g_arena_idle.pop_back();
+      return p;
+    }
+  }
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, cap, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+static void
+grb_arena_give(void* p)
+{
+  std::lock_guard<std::mutex> lk(g_arena_mu);
+  g_arena_idle.push_back(p);
+}
+
 struct grb_ctx
 {
   grb_params p{};
@@ -180,7 +208,9 @@ struct grb_ctx
   cudaEvent_t ra_ready = nullptr, ra_free = nullptr;
   DevBuf<uint8_t> d_raw2;
   const char* pf_host = nullptr; // host range now (being) copied into d_raw2
-  size_t pf_len = 0;
+  size_t pf_len = 0, pf_dev_off = 0;
+  int ra_mapped = -1;            // 1: the host range is device-readable (pinned + mapped)
+  const uint8_t* ra_dev_base = nullptr;
   // ingest scratch
   DevBuf<uint8_t> d_raw;
   DevBuf<uint32_t> d_blk_cnt;
@@ -333,6 +363,41 @@ struct grb_ctx
   {
     err = msg;
     return code;
+  }
+
+  // ---- small host -> device uploads that must not queue behind the ingest read-ahead ----
+  // While a 1 GB read-ahead copy occupies the host-to-device copy engine, every cudaMemcpyAsync of
+  // a descriptor array on the compute stream waits for it (measured: zero overlap).  During that
+  // window descriptors are staged in a pinned, mapped arena and pulled by a small kernel instead.
+  uint8_t* up_host = nullptr;      // pinned + mapped arena
+  uint8_t* up_dev = nullptr;       // its device view
+  size_t up_cap = 0, up_used = 0;  // up_used is reset whenever the stream has been synchronised
+  cudaError_t upload(void* dst, const void* src, size_t bytes, cudaStream_t s)
+  {
+    if (bytes == 0) {
+      return cudaSuccess;
+    }
+    static const bool arena_on = !(getenv("GRB_UPLOAD_ARENA") && strcmp(getenv("GRB_UPLOAD_ARENA"), "0") == 0);
+    const bool window = arena_on && pf_host != nullptr; // a read-ahead copy may be in flight
+    if (window && !up_host) {
+      const size_t cap = (size_t)32 << 20;
+      up_host = (uint8_t*)grb_arena_take(cap); // page-locking 32 MB costs tens of ms: kept per process
+      if (up_host && cudaHostGetDevicePointer((void**)&up_dev, up_host, 0) == cudaSuccess) {
+        up_cap = cap;
+      } else {
+        cudaGetLastError();
+        up_host = nullptr;
+      }
+    }
+    const size_t at = ((up_used + 15) & ~(size_t)15) + ((uintptr_t)dst & 15);
+    if (!window || !up_host || at + bytes > up_cap) {
+      return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+    }
+    memcpy(up_host + at, src, bytes);
+    up_used = at + bytes;
+    k_copy_host<<<8, 256, 0, s>>>((uint8_t*)dst, up_dev + at, bytes);
+    launches += 1;
+    return cudaGetLastError();
   }
   GrbReadsDev reads_dev() const
   {
@@ -612,6 +677,9 @@ grb_destroy(grb_ctx* c)
     cudaEventDestroy(c->ra_ready);
     cudaEventDestroy(c->ra_free);
   }
+  if (c->up_host) {
+    grb_arena_give(c->up_host);
+  }
   grb_pool_free(c->filt.blocks);
   grb_pool_free(c->filt.slots);
   grb_pool_free(c->d_state);
@@ -810,6 +878,7 @@ grb_reads_readahead(grb_ctx* c, const char* base, size_t total)
   c->ra_base = base;
   c->ra_total = base ? total : 0;
   c->pf_host = nullptr;
+  c->ra_mapped = -1;
   return GRB_OK;
 }
 
@@ -836,7 +905,7 @@ grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_
   if (c->pf_host && bytes >= c->pf_host && bytes + n <= c->pf_host + c->pf_len) {
     // the chunk was read ahead: a device-to-device copy re-aligns it to the start of d_raw
     GRB_CUDA(c, cudaStreamWaitEvent(s, c->ra_ready, 0));
-    GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, c->d_raw2.p + (bytes - c->pf_host), n,
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, c->d_raw2.p + c->pf_dev_off + (bytes - c->pf_host), n,
                                 cudaMemcpyDeviceToDevice, s));
   } else {
     GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, bytes, n, cudaMemcpyHostToDevice, s));
@@ -856,11 +925,34 @@ grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_
     if (len > c->d_raw2.cap) {
       GRB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
       c->d_raw2.release();
-      GRB_CUDA(c, c->d_raw2.reserve(n + 2 * kOverlap, 0, s));
+      GRB_CUDA(c, c->d_raw2.reserve(n + 2 * kOverlap + 16, 0, s));
     }
     GRB_CUDA(c, cudaEventRecord(c->ra_free, s)); // d_raw2 is free once the copy above has run
     GRB_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ra_free, 0));
-    GRB_CUDA(c, cudaMemcpyAsync(c->d_raw2.p, lo, len, cudaMemcpyHostToDevice, c->copy_stream));
+    // default: the copy engine (full PCIe rate; the descriptor uploads of the launches that run
+    // meanwhile go through grb_ctx::upload).  GRB_READAHEAD_KERNEL=1 pulls the bytes with a copy
+    // kernel from pinned + mapped host memory instead (measured slower: ~40 GB/s against 51)
+    c->pf_dev_off = 0;
+    const uint8_t* dev_view = nullptr;
+    if (c->ra_mapped < 0) {
+      cudaPointerAttributes pa{};
+      const char* e = getenv("GRB_READAHEAD_KERNEL");
+      c->ra_mapped = 0;
+      if ((e && strcmp(e, "1") == 0) && cudaPointerGetAttributes(&pa, c->ra_base) == cudaSuccess &&
+          pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+        c->ra_mapped = 1;
+        c->ra_dev_base = (const uint8_t*)pa.devicePointer;
+      }
+      cudaGetLastError();
+    }
+    if (c->ra_mapped == 1) {
+      dev_view = c->ra_dev_base + (lo - c->ra_base);
+      c->pf_dev_off = (size_t)((uintptr_t)dev_view & 15);
+      k_copy_host<<<64, 256, 0, c->copy_stream>>>(c->d_raw2.p + c->pf_dev_off, dev_view, len);
+      c->launches += 1;
+    } else {
+      GRB_CUDA(c, cudaMemcpyAsync(c->d_raw2.p, lo, len, cudaMemcpyHostToDevice, c->copy_stream));
+    }
     GRB_CUDA(c, cudaEventRecord(c->ra_ready, c->copy_stream));
     c->pf_host = lo;
     c->pf_len = len;
@@ -933,12 +1025,10 @@ grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_
     c->h_word_off[old + i] = c->n_words + woff[i];
     c->h_flags[old + i] = c->h_meta[old + i].non_acgt ? 4 : 0;
   }
-  GRB_CUDA(c, cudaMemcpyAsync(c->d_word_off.p + old, c->h_word_off.data() + old, n_rec * 8,
-                              cudaMemcpyHostToDevice, s));
-  GRB_CUDA(c, cudaMemcpyAsync(c->d_len.p + old, c->h_len.data() + old, n_rec * 4,
-                              cudaMemcpyHostToDevice, s));
-  GRB_CUDA(c, cudaMemcpyAsync(c->d_flags.p + old, c->h_flags.data() + old, n_rec,
-                              cudaMemcpyHostToDevice, s));
+  c->up_used = 0; // the stream was synchronised above: earlier arena contents have been consumed
+  GRB_CUDA(c, c->upload(c->d_word_off.p + old, c->h_word_off.data() + old, n_rec * 8, s));
+  GRB_CUDA(c, c->upload(c->d_len.p + old, c->h_len.data() + old, n_rec * 4, s));
+  GRB_CUDA(c, c->upload(c->d_flags.p + old, c->h_flags.data() + old, n_rec, s));
   c->toc();
   GRB_CUDA(c, cudaGetLastError());
   c->n_reads += n_rec;
@@ -968,9 +1058,9 @@ grb_reads_set_flags(grb_ctx* c, uint64_t first, uint64_t count, const uint8_t* f
   for (uint64_t i = 0; i < count; ++i) {
     c->h_flags[first + i] = (uint8_t)((c->h_flags[first + i] & 4u) | (flags[i] & 3u));
   }
-  GRB_CUDA(c, cudaMemcpyAsync(c->d_flags.p + first, c->h_flags.data() + first, count,
-                              cudaMemcpyHostToDevice, c->stream));
+  GRB_CUDA(c, c->upload(c->d_flags.p + first, c->h_flags.data() + first, count, c->stream));
   GRB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->up_used = 0;
   return GRB_OK;
 }
 
@@ -1131,10 +1221,8 @@ grb_build_bitvector_range(grb_ctx* c, uint64_t first, uint64_t count)
   if (!chunk_read.empty()) {
     GRB_CUDA(c, c->d_chunk_read.reserve(chunk_read.size(), 0, s));
     GRB_CUDA(c, c->d_chunk_first.reserve(c->n_reads, 0, s));
-    GRB_CUDA(c, cudaMemcpyAsync(c->d_chunk_read.p, chunk_read.data(), chunk_read.size() * 4,
-                                cudaMemcpyHostToDevice, s));
-    GRB_CUDA(c, cudaMemcpyAsync(c->d_chunk_first.p, chunk_first.data(), c->n_reads * 8,
-                                cudaMemcpyHostToDevice, s));
+    GRB_CUDA(c, c->upload(c->d_chunk_read.p, chunk_read.data(), chunk_read.size() * 4, s));
+    GRB_CUDA(c, c->upload(c->d_chunk_first.p, chunk_first.data(), c->n_reads * 8, s));
     c->tic();
     // Partitioned fill (kernels_filter.cuh): worth it once the vector outgrows L2; the direct
     // kernel stays for small filters, for h > 4 and for A/B runs (GRB_FILL=direct|part).

@@ -240,3 +240,40 @@ k_phred(const uint8_t* __restrict__ buf, uint64_t chunk_base, grb_read_meta* __r
   meta[r].phred_first_half_sum = first;
   meta[r].phred_total_sum = total;
 }
+
+// Host -> device copy done by a few CTAs reading mapped pinned host memory over PCIe, used for the
+// ingest read-ahead: it leaves the copy engine free, so the small descriptor uploads of the decode
+// and pass-1 launches that run meanwhile are not queued behind a 1 GB transfer (measured: with
+// cudaMemcpyAsync for the read-ahead, pass 1 under the ingest overlapped nothing).
+// src and dst must have the same alignment modulo 16.
+__global__ void __launch_bounds__(256)
+k_copy_host(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint64_t n)
+{
+  const uint64_t mis = (16 - ((uintptr_t)src & 15)) & 15;
+  const uint64_t head = mis < n ? mis : n;
+  const uint64_t body = (n - head) / 16;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t nth = (uint64_t)gridDim.x * blockDim.x;
+  if (tid < head) {
+    dst[tid] = src[tid];
+  }
+  const uint64_t tail0 = head + body * 16;
+  if (tid < n - tail0) {
+    dst[tail0 + tid] = src[tail0 + tid];
+  }
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+  uint4* d4 = reinterpret_cast<uint4*>(dst + head);
+  uint64_t i = tid;
+  for (; i + 3 * nth < body; i += 4 * nth) { // four 16-byte PCIe reads in flight per thread
+    const uint4 a = __ldcs(s4 + i), b = __ldcs(s4 + i + nth), c = __ldcs(s4 + i + 2 * nth),
+                d = __ldcs(s4 + i + 3 * nth);
+    d4[i] = a;
+    d4[i + nth] = b;
+    d4[i + 2 * nth] = c;
+    d4[i + 3 * nth] = d;
+  }
+  for (; i < body; i += nth) {
+    d4[i] = __ldcs(s4 + i);
+  }
+}
+

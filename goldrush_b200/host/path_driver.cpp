@@ -220,6 +220,11 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   } guard{ ctx };
   auto fail = [&](int code) { return set_err(err, err_cap, grb_last_error(ctx), code); };
 
+  bool early = false; // pass 1 already done chunk by chunk during the ingest
+  uint64_t early_bits = 0;
+  double early_ms = 0;
+  std::vector<uint8_t> early_flags;
+
   // ---- K1: one pass over the file ----
   if (n == 0 || data[0] != '@') {
     log("Gold Path requires fastq format\n"); // goldrush_path.cpp:247-250
@@ -234,13 +239,37 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     if ((rc = grb_reads_readahead(ctx, data, n)) != GRB_OK) { // next chunk's copy under this one's decode
       return fail(rc);
     }
+    // Pass 1 under the ingest: when the filter size and the Phred threshold do not depend on the
+    // whole file (-P given, no --ntcard), a read's pass-1 verdict (goldrush_path.cpp:261-301) only
+    // needs its own record, so each chunk's reads are hashed into the bit vector while the next
+    // chunk is still crossing PCIe.  The regular filter stage below re-derives the same flags.
+    {
+      int c_rank = 0, c_world = 1;
+      grb_comm_info(ctx, &c_rank, &c_world);
+      const char* e = getenv("GRB_EARLY_PASS1");
+      early = p.phred_min != 0 && (p.hash_universe != 0 || !o->ntcard) && c_world == 1 &&
+              !(e && strcmp(e, "0") == 0);
+    }
+    if (early) {
+      const uint64_t hu = p.hash_universe
+                            ? p.hash_universe
+                            : grb_default_hash_universe(p.weight, p.genome_size, p.hash_num);
+      early_bits = grb_calc_optimal_size(hu, 1, p.occupancy);
+      if ((rc = grb_filter_alloc(ctx, early_bits)) != GRB_OK) {
+        return fail(rc);
+      }
+    }
+    uint64_t early_done = 0;
+    std::vector<grb_read_meta> cm;
     while (off < n) {
       const size_t len = std::min(kChunk, n - off);
       const int final = off + len == n;
       size_t used = 0;
+      const double t_c0 = now_ms();
       if ((rc = grb_reads_ingest_fastq(ctx, data + off, len, final, &used)) != GRB_OK) {
         return fail(rc);
       }
+      const double t_c1 = now_ms();
       R.ms_ingest += grb_last_device_ms(ctx);
       if (used == 0) {
         if (final) {
@@ -249,6 +278,35 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
         return set_err(err, err_cap, "FASTQ record larger than the 1 GiB ingest chunk", GRB_ERR_ARG);
       }
       off += used;
+      if (early) {
+        const uint64_t now = grb_reads_count(ctx), cnt = now - early_done;
+        if (cnt) {
+          cm.resize(cnt);
+          if ((rc = grb_reads_get_meta(ctx, early_done, cnt, cm.data())) != GRB_OK) {
+            return fail(rc);
+          }
+          early_flags.resize(now, 0);
+          for (uint64_t i = 0; i < cnt; ++i) {
+            uint32_t a = 0, d = 0;
+            grb_phred_finalize(cm[i].phred_first_half_sum, cm[i].phred_total_sum, cm[i].qual_len, &a, &d);
+            early_flags[early_done + i] = (cm[i].len >= p.min_length && a >= p.phred_min &&
+                                           d < p.phred_delta && !cm[i].non_acgt)
+                                            ? GRB_READ_PASS1
+                                            : 0;
+          }
+          if ((rc = grb_reads_set_flags(ctx, early_done, cnt, early_flags.data() + early_done)) != GRB_OK ||
+              (rc = grb_build_bitvector_range(ctx, early_done, cnt)) != GRB_OK) {
+            log("%s\n", grb_last_error(ctx));
+            return fail(rc);
+          }
+          early_ms += grb_last_device_ms(ctx);
+          early_done = now;
+        }
+      }
+      if (timing && getenv("GRB_TIMING")[0] == '2') {
+        fprintf(stderr, "[grb chunk] ingest %.1f ms (device %.1f)  early pass 1 %.1f ms\n", t_c1 - t_c0,
+                grb_last_device_ms(ctx), now_ms() - t_c1);
+      }
     }
     grb_reads_readahead(ctx, nullptr, 0);
   }
@@ -452,7 +510,13 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   log("allocating bit vector\n");
   const uint64_t filter_bits = grb_calc_optimal_size(p.hash_universe, 1, p.occupancy);
   log("m_filterSize: %llu\n", (unsigned long long)filter_bits);
-  if ((rc = grb_filter_alloc(ctx, filter_bits)) != GRB_OK) {
+  if (early) { // the early pass must have used this very size and these very flags
+    early = filter_bits == early_bits && early_flags.size() == nreads;
+    for (uint64_t i = 0; early && i < nreads; ++i) {
+      early = (flags[i] & GRB_READ_PASS1) == early_flags[i];
+    }
+  }
+  if (!early && (rc = grb_filter_alloc(ctx, filter_bits)) != GRB_OK) {
     return fail(rc);
   }
   R.filter_bits = filter_bits;
@@ -462,11 +526,15 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   if (nreads && (rc = grb_reads_set_flags(ctx, 0, nreads, flags.data())) != GRB_OK) {
     return fail(rc);
   }
-  if ((rc = grb_build_bitvector(ctx)) != GRB_OK) {
-    log("%s\n", grb_last_error(ctx));
-    return fail(rc);
+  if (early) {
+    R.ms_pass1 = early_ms;
+  } else {
+    if ((rc = grb_build_bitvector(ctx)) != GRB_OK) {
+      log("%s\n", grb_last_error(ctx));
+      return fail(rc);
+    }
+    R.ms_pass1 = grb_last_device_ms(ctx);
   }
-  R.ms_pass1 = grb_last_device_ms(ctx);
   if (o->verbose) {
     log("num_passed_reads: %llu\nnum_reads: %llu\nnum_reads - num_passed_reads: %llu\n"
         "num_reads - num_passed_reads / num_reads: %.0f\nnum_reads_skipped_by_phred: %llu\n"
