@@ -152,6 +152,7 @@ def lib():
         "grb_comm_init": (i32, [vp, i32, i32, i32]),
         "grb_comm_destroy": (None, []),
         "grb_comm_info": (i32, [vp, P(i32), P(i32)]),
+        "grb_bitvector_or_reduce": (i32, [vp]),
         "grb_bitvector_device": (i32, [vp, P(vp), P(u64)]),
         "grb_or_words": (i32, [vp, vp, vp, u64]),
         "grb_sync": (i32, [vp]),
@@ -349,6 +350,9 @@ class Engine:
             self._chk(self._L.grb_build_bitvector(self._h))
         else:
             self._chk(self._L.grb_build_bitvector_range(self._h, first, count))
+
+    def bitvector_or_reduce(self):
+        self._chk(self._L.grb_bitvector_or_reduce(self._h))
 
     def finalize_bitvector(self):
         pop = C.c_uint64()

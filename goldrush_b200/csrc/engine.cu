@@ -592,6 +592,9 @@ grb_create(const grb_params* p, grb_ctx** out)
     return bail(GRB_ERR_CUDA, std::string("CUDA init: ") + cudaGetErrorString(e));
   }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+  // reads per speculative batch: two per SM, so that the per-read phase of the commit kernel (one
+  // CTA per read, one CTA per SM) splits evenly; 296 on B200 (A/B 64 .. 800: profiles/README.md)
+  c->batch_reads = (uint32_t)std::min(1024, std::max(64, 2 * c->sm_count));
   // L2 -> DRAM fetch granularity: measured on B200 (profiles/sector_roofline_r01.json, ncu
   // dram__sectors_read of k2_query) every L2 miss moves a whole 128-byte line whatever this limit
   // says, and asking for 32 bytes only slowed the L2-sized structures down.  The device default is
@@ -1351,6 +1354,26 @@ or_reduce_bitvector(grb_ctx* c)
   c->kend(GRB_K_GATHER, n_launch);
   GRB_CUDA(c, cudaGetLastError());
   return GRB_OK;
+}
+
+// OR-reduce of the replicas' bit vectors for callers that sharded pass 1 themselves with
+// grb_build_bitvector_range (grb_run_path does, chunk by chunk under the ingest); no-op on one GPU
+int
+grb_bitvector_or_reduce(grb_ctx* c)
+{
+  cudaSetDevice(c->device);
+  if (!c->filter_alloc || c->finalized) {
+    return c->fail(GRB_ERR_STATE, "grb_bitvector_or_reduce: needs grb_filter_alloc and no finalize yet");
+  }
+  if (!c->comm) {
+    return GRB_OK;
+  }
+  c->tic();
+  const int rc = or_reduce_bitvector(c);
+  if (rc == GRB_OK) {
+    c->toc();
+  }
+  return rc;
 }
 
 int

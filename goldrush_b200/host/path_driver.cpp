@@ -220,6 +220,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   } guard{ ctx };
   auto fail = [&](int code) { return set_err(err, err_cap, grb_last_error(ctx), code); };
 
+  int c_world_now = 1;
   bool early = false; // pass 1 already done chunk by chunk during the ingest
   uint64_t early_bits = 0;
   double early_ms = 0;
@@ -243,12 +244,12 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     // whole file (-P given, no --ntcard), a read's pass-1 verdict (goldrush_path.cpp:261-301) only
     // needs its own record, so each chunk's reads are hashed into the bit vector while the next
     // chunk is still crossing PCIe.  The regular filter stage below re-derives the same flags.
+    int c_rank = 0, c_world = 1; // several GPUs: each rank hashes its share of every chunk
+    grb_comm_info(ctx, &c_rank, &c_world);
+    c_world_now = c_world;
     {
-      int c_rank = 0, c_world = 1;
-      grb_comm_info(ctx, &c_rank, &c_world);
       const char* e = getenv("GRB_EARLY_PASS1");
-      early = p.phred_min != 0 && (p.hash_universe != 0 || !o->ntcard) && c_world == 1 &&
-              !(e && strcmp(e, "0") == 0);
+      early = p.phred_min != 0 && (p.hash_universe != 0 || !o->ntcard) && !(e && strcmp(e, "0") == 0);
     }
     if (early) {
       const uint64_t hu = p.hash_universe
@@ -294,8 +295,10 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
                                             ? GRB_READ_PASS1
                                             : 0;
           }
+          const uint64_t my_lo = early_done + cnt * (uint64_t)c_rank / (uint64_t)c_world;
+          const uint64_t my_hi = early_done + cnt * (uint64_t)(c_rank + 1) / (uint64_t)c_world;
           if ((rc = grb_reads_set_flags(ctx, early_done, cnt, early_flags.data() + early_done)) != GRB_OK ||
-              (rc = grb_build_bitvector_range(ctx, early_done, cnt)) != GRB_OK) {
+              (rc = grb_build_bitvector_range(ctx, my_lo, my_hi - my_lo)) != GRB_OK) {
             log("%s\n", grb_last_error(ctx));
             return fail(rc);
           }
@@ -527,7 +530,10 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     return fail(rc);
   }
   if (early) {
-    R.ms_pass1 = early_ms;
+    if ((rc = grb_bitvector_or_reduce(ctx)) != GRB_OK) { // no-op on one GPU
+      return fail(rc);
+    }
+    R.ms_pass1 = early_ms + (c_world_now > 1 ? grb_last_device_ms(ctx) : 0.0);
   } else {
     if ((rc = grb_build_bitvector(ctx)) != GRB_OK) {
       log("%s\n", grb_last_error(ctx));

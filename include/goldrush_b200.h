@@ -229,6 +229,10 @@ int grb_insert_tiles(grb_ctx* ctx, uint64_t read_idx, uint32_t tile_start, uint3
 int grb_comm_unique_id(uint8_t* out128);
 int grb_comm_init(const uint8_t* id128, int rank, int world, int device);
 void grb_comm_destroy(void);
+/* OR-reduce of the ranks' bit vectors, for callers that shard pass 1 themselves with
+ * grb_build_bitvector_range (every rank must call it, before grb_finalize_bitvector); no-op for a
+ * context without communicator */
+int grb_bitvector_or_reduce(grb_ctx* ctx);
 /* ctx == NULL: the process-wide communicator; else what this context uses (0 / 1 if unsharded) */
 int grb_comm_info(const grb_ctx* ctx, int* rank, int* world);
 
