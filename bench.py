@@ -345,6 +345,19 @@ def bench_ours(args, w):
                    if args.workload == "cfg2" else None)
     except (OSError, KeyError, ValueError):
         pass
+    # third denominator: the filter's own probe sequence without hashing / voting, measured over
+    # footprints by tools/probe_bench.py (cfg5, profiles/probe_bench_r01.jsonl)
+    probe_peak = None
+    try:
+        footprint_gb = ((filter_bits + 191) // 192 * 32 + (int(pop) + 1) * 16) / 1e9
+        rows = [json.loads(l) for l in open(os.path.join(ROOT, "profiles", "probe_bench_r01.jsonl"))]
+        rows = [r for r in rows if r.get("h") == PARAMS["hash_num"] and "query_gprobes_per_s" in r]
+        near = min(rows, key=lambda r: abs(r["footprint_gb"] - footprint_gb))
+        probe_peak = {"gprobes_per_s": near["query_gprobes_per_s"], "at_footprint_gb": near["footprint_gb"],
+                      "footprint_gb": round(footprint_gb, 2)}
+    except (OSError, ValueError, KeyError):
+        pass
+    gprobes = probes_per_step * args.steps / (q_ms * 1e-3) / 1e9 if q_ms > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": "k2_query", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
@@ -352,7 +365,9 @@ def bench_ours(args, w):
                 "launches_per_step": q_n // max(1, args.steps),
                 "avg_launch_us": 1e3 * q_ms / max(1, q_n), "traffic": traffic,
                 "random_sector_peak": sector_peak,
-                "frac_of_random_sector_peak": achieved / sector_peak if sector_peak else None}
+                "frac_of_random_sector_peak": achieved / sector_peak if sector_peak else None,
+                "gprobes_per_s": gprobes, "probe_microbench": probe_peak,
+                "frac_of_probe_microbench": (gprobes / probe_peak["gprobes_per_s"]) if probe_peak else None}
     del eng
 
     # ---- e2e: the public whole-stage call on the pinned host FASTQ ----

@@ -55,6 +55,12 @@ class PathStats(C.Structure):
     ]
 
 
+class ProbeBenchResult(C.Structure):
+    _fields_ = [("query_ms", C.c_double), ("insert_ms", C.c_double), ("probes", C.c_uint64),
+                ("pop", C.c_uint64), ("filter_bits", C.c_uint64), ("footprint_bytes", C.c_uint64),
+                ("checksum", C.c_uint64), ("keys_filled", C.c_uint64), ("probes_missed", C.c_uint64)]
+
+
 class RunOptions(C.Structure):
     _fields_ = [
         ("params", Params), ("seed_preset", C.c_char_p), ("prefix", C.c_char_p),
@@ -161,6 +167,7 @@ def lib():
         "grb_profile_enable": (i32, [vp, i32]),
         "grb_kernel_time": (i32, [vp, i32, P(dbl), P(u64)]),
         "grb_commit_profile": (i32, [vp, P(u64)]),
+        "grb_probe_bench": (i32, [vp, u64, dbl, u32, u64, u64, i32, P(ProbeBenchResult)]),
         "grb_run_path": (i32, [P(RunOptions), vp, sz, P(RunResult), C.c_char_p, sz]),
         "grb_run_two_stage": (i32, [P(RunOptions), P(RunOptions), vp, sz, P(RunResult), P(RunResult),
                                     C.c_char_p, sz]),
@@ -353,6 +360,13 @@ class Engine:
 
     def bitvector_or_reduce(self):
         self._chk(self._L.grb_bitvector_or_reduce(self._h))
+
+    def probe_bench(self, filter_bits, fill, h, n_probes=1 << 28, seed=42, reps=3):
+        """grb_probe_bench: query / insert probe throughput at one filter size (cfg5)."""
+        out = ProbeBenchResult()
+        self._chk(self._L.grb_probe_bench(self._h, filter_bits, fill, h, n_probes, seed, reps,
+                                          C.byref(out)))
+        return out
 
     def finalize_bitvector(self):
         pop = C.c_uint64()

@@ -9,6 +9,7 @@
 #include "kernels_batch2.cuh"
 #include "kernels_fix.cuh"
 #include "comm.cuh"
+#include "kernels_probe.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1500,6 +1501,81 @@ grb_or_words(grb_ctx* c, void* dst, const void* src, uint64_t n_words)
     (uint64_t*)dst, (const uint64_t*)src, n_words);
   c->launches += 1;
   GRB_CUDA(c, cudaGetLastError());
+  return GRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// probe microbenchmark (kernels_probe.cuh)
+// ------------------------------------------------------------------------------------------
+int
+grb_probe_bench(grb_ctx* c, uint64_t filter_bits, double fill, uint32_t h, uint64_t n_probes,
+                uint64_t seed, int reps, grb_probe_bench_result* out)
+{
+  cudaSetDevice(c->device);
+  if (h == 0 || h > GRB_MAX_PATTERNS || !(fill > 0.0 && fill < 0.95) || reps < 1 || n_probes < h) {
+    return c->fail(GRB_ERR_ARG, "grb_probe_bench: h in 1..8, fill in (0, 0.95), reps >= 1");
+  }
+  memset(out, 0, sizeof *out);
+  int rc = grb_filter_alloc(c, filter_bits);
+  if (rc != GRB_OK) {
+    return rc;
+  }
+  cudaStream_t s = c->stream;
+  // keys whose h hashes set a fraction `fill` of the bits: 1 - exp(-n h / m) = fill
+  const uint64_t n_fill = std::max<uint64_t>(1, (uint64_t)(-log(1.0 - fill) * (double)filter_bits / h));
+  k_probe_fill<<<c->sm_count * 16, 256, 0, s>>>(c->filt, n_fill, h, seed);
+  c->launches += 1;
+  uint64_t pop = 0;
+  if ((rc = grb_finalize_bitvector(c, &pop)) != GRB_OK) {
+    return rc;
+  }
+  k_probe_ids<<<c->sm_count * 16, 256, 0, s>>>(c->filt.slots, pop, seed ^ 0x5bd1e995u);
+  c->launches += 1;
+  DevBuf<unsigned long long> sum;
+  GRB_CUDA(c, sum.reserve(2, 0, s));
+  GRB_CUDA(c, cudaMemsetAsync(sum.p, 0, 16, s));
+  const uint64_t n_keys = n_probes / h;
+  const unsigned grid = (unsigned)c->sm_count * 16;
+  cudaEvent_t e0 = c->prof_event(), e1 = c->prof_event();
+  float best_q = 1e30f, best_i = 1e30f;
+  for (int r = 0; r <= reps; ++r) { // first round is the warm-up
+    cudaEventRecord(e0, s);
+    k_probe_query<<<grid, 256, 0, s>>>(c->filt, n_keys, n_fill, h, seed, ~seed + 977ull * r * n_keys, sum.p);
+    cudaEventRecord(e1, s);
+    GRB_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r) {
+      best_q = std::min(best_q, ms);
+    }
+  }
+  for (int r = 0; r <= reps; ++r) {
+    cudaEventRecord(e0, s);
+    k_probe_insert<<<grid, 256, 0, s>>>(c->filt, n_keys, n_fill, h, seed, seed * 31 + 131ull * r * n_keys, 7u + r);
+    cudaEventRecord(e1, s);
+    GRB_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r) {
+      best_i = std::min(best_i, ms);
+    }
+  }
+  c->launches += 2 * (uint64_t)(reps + 1);
+  c->prof_free.push_back(e0);
+  c->prof_free.push_back(e1);
+  unsigned long long hsum[2] = { 0, 0 };
+  GRB_CUDA(c, cudaMemcpyAsync(hsum, sum.p, 16, cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  GRB_CUDA(c, cudaGetLastError());
+  out->query_ms = best_q;
+  out->insert_ms = best_i;
+  out->probes = n_keys * h;
+  out->pop = pop;
+  out->filter_bits = filter_bits;
+  out->footprint_bytes = c->filt.n_blocks * 32 + (pop + 1) * sizeof(GrbSlot);
+  out->checksum = hsum[0];
+  out->probes_missed = hsum[1];
+  out->keys_filled = n_fill;
   return GRB_OK;
 }
 

@@ -269,6 +269,29 @@ int grb_profile_enable(grb_ctx* ctx, int on);
 int grb_commit_profile(grb_ctx* ctx, uint64_t* out10);
 int grb_kernel_time(grb_ctx* ctx, int kclass, double* ms, uint64_t* n_launches);
 
+/* ---- miBF probe microbenchmark (BASELINE.json configs[4]) ----
+ * Builds a filter of filter_bits bits on this context (any earlier filter is dropped), sets a
+ * fraction `fill` of them from synthetic keys (splitmix64), gives half of the ID slots an ID, then
+ * times the product path's probe sequences over n_probes probes (n_probes / h keys drawn from the
+ * inserted ones, so every probe meets a set bit): query = h block probes (bit + rank from one
+ * 32-byte block) followed by the h slot reads; insert = the same block probes followed by the
+ * reservoir read-modify-write of each slot (MIBFConstructSupport.hpp:271-282).  Best of `reps`
+ * timed launches each, CUDA events.  Needs about filter_bits / 6 + 16 * fill * filter_bits bytes. */
+typedef struct grb_probe_bench_result
+{
+  double query_ms;
+  double insert_ms;
+  uint64_t probes;
+  uint64_t pop;
+  uint64_t filter_bits;
+  uint64_t footprint_bytes; /* filter blocks + ID slots */
+  uint64_t checksum;        /* sum of the IDs read by the query launches */
+  uint64_t keys_filled;
+  uint64_t probes_missed;   /* keys of the query launches that met a clear bit: must be 0 */
+} grb_probe_bench_result;
+int grb_probe_bench(grb_ctx* ctx, uint64_t filter_bits, double fill, uint32_t h, uint64_t n_probes,
+                    uint64_t seed, int reps, grb_probe_bench_result* out);
+
 /* ---- whole stage: what goldrush_path.cpp main() does between option parsing and exit ----
  * (goldrush_path.cpp:1096-1275).  fastq = the whole input file in host memory.  Writes
  * <prefix>_N.fq / <prefix>.fa exactly as the reference.  log may be NULL (else a FILE*-like

@@ -178,6 +178,20 @@ def test_partitioned_fill_equals_oracle(h, bits, env, monkeypatch):
         assert e.finalize_bitvector() == f.setup()
 
 
+def test_probe_microbenchmark_builds_the_filter_it_claims():
+    """grb_probe_bench (cfg5): the synthetic filter reaches the requested share of set bits, every
+    probe of the timed launches meets a set bit (the checksum carries no miss marker), and half of
+    the slots hold an ID."""
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, 3)
+    with grb.Engine(seeds, genome_size=1000000, weight=16) as e:
+        for h in (1, 3, 5):
+            r = e.probe_bench(50_000_000 + 64, 0.3, h, n_probes=1 << 20, reps=2)
+            assert abs(r.pop / r.filter_bits - 0.3) < 0.005
+            assert r.probes == ((1 << 20) // h) * h and r.query_ms > 0 and r.insert_ms > 0
+            assert r.checksum > 0 and r.probes_missed == 0
+            assert r.footprint_bytes == ((r.filter_bits + 191) // 192) * 32 + (r.pop + 1) * 16
+
+
 def _tile_hashes(seq, t, T, k, seeds):
     tile = seq[t * T:t * T + T + k - 1]
     return ou.hash_sequence(tile, seeds)
