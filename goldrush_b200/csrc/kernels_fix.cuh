@@ -134,6 +134,23 @@ grb3_block_append(bool take, uint32_t item, uint32_t item2, uint32_t* list, uint
   }
 }
 
+// counter += 1 for every calling lane, one atomic per group of lanes that name the same counter;
+// returns the caller's slot.  Call from divergent code: the group is whoever is here right now.
+__device__ __forceinline__ uint32_t
+grb3_agg_inc(uint32_t* counter)
+{
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, (unsigned long long)counter);
+  const unsigned lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if ((int)lane == leader) {
+    base = atomicAdd(counter, (uint32_t)__popc(peers));
+  }
+  base = __shfl_sync(peers, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1u));
+}
+
 __device__ __forceinline__ uint32_t
 grb3_set_mask(uint32_t n_cand, uint32_t cap_mask)
 {
@@ -308,7 +325,7 @@ k3_open(GrbFilterDev filt, GrbB3 b3, const GrbSelState* __restrict__ state)
       continue;
     }
     const uint64_t rank = b3.ix_tab[i];
-    const uint32_t sidx = atomicAdd(&b3.counters[GRB_CTR_SHARED], 1u);
+    const uint32_t sidx = grb3_agg_inc(&b3.counters[GRB_CTR_SHARED]);
     b3.ix_sidx[i] = sidx;
     const uint2 raw = __ldcg(reinterpret_cast<const uint2*>(&filt.slots[rank]));
     GrbShared3 e;
@@ -342,7 +359,7 @@ k3_conf(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
     }
     const uint32_t sidx = b3.ix_sidx[slot];
     const uint32_t probe = b3.t_probe[li];
-    const uint32_t ci = atomicAdd(&b3.counters[GRB_CTR_CONF], 1u);
+    const uint32_t ci = grb3_agg_inc(&b3.counters[GRB_CTR_CONF]);
     b3.c_probe[ci] = probe;
     b3.c_sidx[ci] = sidx;
     const GrbProbeAt a = grb2_probe_at(reads, prm, bd, probe);
@@ -355,7 +372,7 @@ k3_conf(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
       const uint32_t g = a.bt * T + ff;
       const uint32_t bit = 1u << (g & 31);
       if (!(atomicOr(&b3.fbits[g >> 5], bit) & bit)) {
-        const uint32_t at = atomicAdd(&b3.fl_n[a.b], 1u);
+        const uint32_t at = grb3_agg_inc(&b3.fl_n[a.b]);
         b3.fl[(uint64_t)bd.tile_first[a.b] * T + at] = (a.t << 20) | ff;
       }
     }
