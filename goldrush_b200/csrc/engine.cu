@@ -855,6 +855,15 @@ grb_reads_clear(grb_ctx* c)
   c->h_word_off.clear();
   c->h_flags.clear();
   c->h_meta.clear();
+  // a read-ahead copy still in flight belongs to the input that is being dropped
+  if (c->copy_stream) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->copy_stream);
+  }
+  c->ra_base = nullptr;
+  c->ra_total = 0;
+  c->pf_host = nullptr;
+  c->ra_mapped = -1;
 }
 
 int
