@@ -248,6 +248,7 @@ struct grb_ctx
   size_t query_smem = 0, query2_smem = 0;
   // batch engine (kernels_batch.cuh)
   bool batch_mode = true;
+  bool batch_reads_fixed = false; // GRB_BATCH_READS given: no adaptation to the genome size
   uint32_t batch_reads = 320;  // reads per speculative batch (A/B on B200: 64..800, profiles/README.md)
   uint32_t batch_tiles = 8192; // tile budget per batch (a single longer read still forms a batch)
   uint32_t dirty_bits_log2 = 28;
@@ -624,6 +625,7 @@ grb_create(const grb_params* p, grb_ctx** out)
     const long v = strtol(e, nullptr, 10);
     if (v > 0 && v <= 65536) {
       c->batch_reads = (uint32_t)v;
+      c->batch_reads_fixed = true;
     }
   }
   {
@@ -2510,7 +2512,15 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
   const uint64_t end = first + count;
   uint64_t i = first;
   uint64_t stop_at = c->sel_finished ? first : end; // reads at or past it were never reached
-  const uint64_t kChunk = c->batch_mode ? 4ull * c->batch_reads : 256;
+  // A batch that covers a large part of the genome shares most of its ranks with itself and the
+  // ordered commit degenerates: keep a batch below about half the genome (cfg1, 5 Mbp: 296 reads
+  // per batch 57 ms, 128 reads 41 ms; cfg2 is capped by two reads per SM either way).
+  uint32_t batch_reads = c->batch_reads;
+  if (!c->batch_reads_fixed && max_len > 0 && c->p.genome_size > 0) {
+    const uint64_t fit = c->p.genome_size / (2 * max_len);
+    batch_reads = (uint32_t)std::min<uint64_t>(batch_reads, std::max<uint64_t>(32, fit));
+  }
+  const uint64_t kChunk = c->batch_mode ? 4ull * batch_reads : 256;
   while (i < end && !c->sel_finished) {
     uint64_t launched = 0, j = i;
     if (c->batch_mode) {
@@ -2529,7 +2539,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
           continue;
         }
         const uint32_t tiles = (uint32_t)(c->h_len[j] / T);
-        if (bp.batches.empty() || bp.batches.back().nb >= c->batch_reads ||
+        if (bp.batches.empty() || bp.batches.back().nb >= batch_reads ||
             (bp.batches.back().n_bt && bp.batches.back().n_bt + tiles > tile_budget)) {
           if (!bp.batches.empty()) {
             bp.tile_first.push_back(bp.batches.back().n_bt);
