@@ -1516,6 +1516,63 @@ grb_or_words(grb_ctx* c, void* dst, const void* src, uint64_t n_words)
 }
 
 // ------------------------------------------------------------------------------------------
+// TEST HOOK: the grouped half-hash evaluation of nthash.cuh (the very functions k2_query and
+// k_fill_part inline: table construction, grb_lo64, grb_group_half, grb_combine) run on the HOST,
+// so that the product's hash formulation is checked against the oracle on a machine without a GPU.
+// out[frame * h + pattern] with the stale-tail rule of multiLensfrHashIterator.hpp:49-68.
+// ACGT (upper case) only.  Nothing in the product path calls this.
+// ------------------------------------------------------------------------------------------
+struct GrbWordArray
+{
+  const uint64_t* w;
+  __host__ __device__ uint64_t operator()(uint64_t i) const { return w[i]; }
+};
+
+int
+grb_test_group_hash_host(const char* const* seeds, uint32_t h, const char* seq, size_t n, uint64_t* out)
+{
+  grb_ctx tmp;
+  for (uint32_t i = 0; i < h; ++i) {
+    tmp.seeds.emplace_back(seeds[i]);
+  }
+  if (h == 0 || build_seed_tables(&tmp) != GRB_OK) {
+    return GRB_ERR_ARG;
+  }
+  const GrbSeedTables& t = tmp.h_seed;
+  if (n < t.k + t.h - 1) {
+    return GRB_ERR_ARG;
+  }
+  uint32_t ng = 0;
+  const std::vector<ulonglong2> tab = build_group_tables(t, &ng);
+  const ulonglong2* tl_ = tab.data();
+  const ulonglong2* tr_ = tab.data() + (size_t)ng * 256;
+  std::vector<uint64_t> words(n / 32 + 4, 0);
+  for (size_t i = 0; i < n; ++i) {
+    uint64_t code;
+    switch (seq[i]) {
+      case 'A': code = 0; break;
+      case 'C': code = 1; break;
+      case 'G': code = 2; break;
+      case 'T': code = 3; break;
+      default: return GRB_ERR_ARG;
+    }
+    words[i >> 5] |= code << (2 * (i & 31));
+  }
+  const GrbWordArray word{ words.data() };
+  const uint64_t frames = n - t.k + 1;
+  for (uint64_t f = 0; f < frames; ++f) {
+    for (uint32_t i = 0; i < t.h; ++i) {
+      const uint64_t n_i = n - (t.k + i) + 1;
+      const uint64_t p = f < n_i ? f : n_i - 1;
+      const ulonglong2 l = grb_group_half(tl_, ng, grb_lo64(word, p));
+      const ulonglong2 r = grb_group_half(tr_, ng, grb_lo64(word, p + t.half + i));
+      out[f * t.h + i] = grb_combine(i, l.x, l.y, r.x, r.y);
+    }
+  }
+  return GRB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
 // probe microbenchmark (kernels_probe.cuh)
 // ------------------------------------------------------------------------------------------
 int

@@ -123,7 +123,7 @@ grb_half_hashes(const GrbSeedTables& t, const GrbWindow& w)
 }
 
 // hash of pattern i at frame f from the left halves at f and the right halves at f + half + i
-__device__ __forceinline__ uint64_t
+__host__ __device__ __forceinline__ uint64_t
 grb_combine(unsigned i, uint64_t fl, uint64_t rl, uint64_t fr, uint64_t rr)
 {
   return (grb_srol(fl, i) ^ fr) + (rl ^ grb_srol(rr, i));
@@ -144,7 +144,7 @@ grb_combine(unsigned i, uint64_t fl, uint64_t rl, uint64_t fr, uint64_t rr)
 
 // the 32 bases starting at absolute base index `pos` (LSB first)
 template<typename WordLoader>
-__device__ __forceinline__ uint64_t
+__host__ __device__ __forceinline__ uint64_t
 grb_lo64(WordLoader&& word, uint64_t pos)
 {
   const uint64_t wi = pos >> 5;
@@ -154,11 +154,13 @@ grb_lo64(WordLoader&& word, uint64_t pos)
 }
 
 // out.x ^= first halves, out.y ^= second halves of the table entries picked by the window bytes
-__device__ __forceinline__ ulonglong2
+__host__ __device__ __forceinline__ ulonglong2
 grb_group_half(const ulonglong2* __restrict__ tab, unsigned ng, uint64_t lo)
 {
   ulonglong2 o = make_ulonglong2(0, 0);
+#if defined(__CUDA_ARCH__)
 #pragma unroll
+#endif
   for (unsigned g = 0; g < GRB_MAX_GROUPS; ++g) {
     if (g < ng) {
       const unsigned v = (unsigned)(lo >> (8 * g)) & 0xFFu;

@@ -371,6 +371,12 @@ int grb_test_decide_host(uint32_t n_tiles, const uint32_t* best_id, const uint32
                          uint64_t assigned_max, uint32_t* ids_inserted, uint32_t* out_ids,
                          uint8_t* out_assigned, uint32_t* out_plan);
 
+/* ---- test hook: the grouped half-hash code of csrc/nthash.cuh (what the query and fill kernels
+ * inline) compiled for the host; out[frame * h + pattern], frames = n - k + 1, ACGT only.  Checked
+ * against the oracle's SeedNtHash restatement by the CPU test suite.  Never called by the product. */
+int grb_test_group_hash_host(const char* const* seeds, uint32_t h, const char* seq, size_t n,
+                             uint64_t* out);
+
 #ifdef __cplusplus
 }
 #endif

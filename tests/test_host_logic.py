@@ -170,3 +170,23 @@ def test_synth_generator_is_deterministic_and_thread_independent():
     # generating a sub-range gives the same records
     part = grb.synth_fastq(sp, 5, 3)
     assert part in a
+
+
+@pytest.mark.parametrize("k,w,h,preset", [(22, 16, 3, "1011011110110111101101"), (22, 16, 1, "1011011110110111101101"),
+                                          (20, 12, 2, ""), (24, 18, 4, ""), (32, 20, 5, "")])
+def test_grouped_hash_code_matches_oracle_on_host(k, w, h, preset):
+    """The hash formulation the query / fill kernels use (csrc/nthash.cuh: grouped half-hash tables,
+    grb_lo64, grb_group_half, grb_combine), compiled for the host, against the oracle's SeedNtHash
+    restatement: every frame, every pattern, stale tail included."""
+    import ctypes as C
+    seeds = grb.make_seed_pattern(preset, k, w, h)
+    assert seeds == ou.make_seed_pattern(preset, k, w, h)
+    rng = np.random.default_rng(k * 100 + h)
+    for n in (k + h - 1, k + h + 5, 97, 1000, 5003):
+        seq = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)])
+        want = ou.hash_sequence(seq, seeds)
+        out = np.zeros((n - k + 1) * h, dtype=np.uint64)
+        arr = (C.c_char_p * h)(*[s.encode() for s in seeds])
+        rc = grb.lib().grb_test_group_hash_host(arr, h, seq, n, out.ctypes.data)
+        assert rc == 0
+        assert np.array_equal(out.reshape(-1, h), want), (n, k, h)
