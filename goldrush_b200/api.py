@@ -58,7 +58,8 @@ class PathStats(C.Structure):
 class ProbeBenchResult(C.Structure):
     _fields_ = [("query_ms", C.c_double), ("insert_ms", C.c_double), ("probes", C.c_uint64),
                 ("pop", C.c_uint64), ("filter_bits", C.c_uint64), ("footprint_bytes", C.c_uint64),
-                ("checksum", C.c_uint64), ("keys_filled", C.c_uint64), ("probes_missed", C.c_uint64)]
+                ("checksum", C.c_uint64), ("keys_filled", C.c_uint64), ("probes_missed", C.c_uint64),
+                ("line_query_ms", C.c_double), ("line_bytes", C.c_uint64)]
 
 
 class RunOptions(C.Structure):

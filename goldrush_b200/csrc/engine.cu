@@ -1617,6 +1617,21 @@ grb_probe_bench(grb_ctx* c, uint64_t filter_bits, double fill, uint32_t h, uint6
       best_q = std::min(best_q, ms);
     }
   }
+  // one-line-per-probe variant over the same memory (the slot array read as 128-byte lines)
+  float best_l = 1e30f;
+  const uint64_t n_lines = (pop + 1) * sizeof(GrbSlot) / 128;
+  for (int r = 0; r <= reps && n_lines > 0; ++r) {
+    cudaEventRecord(e0, s);
+    k_probe_line<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(c->filt.slots), n_lines, n_keys, h,
+                                      seed, seed * 17 + 311ull * r * n_keys, sum.p);
+    cudaEventRecord(e1, s);
+    GRB_CUDA(c, cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r) {
+      best_l = std::min(best_l, ms);
+    }
+  }
   for (int r = 0; r <= reps; ++r) {
     cudaEventRecord(e0, s);
     k_probe_insert<<<grid, 256, 0, s>>>(c->filt, n_keys, n_fill, h, seed, seed * 31 + 131ull * r * n_keys, 7u + r);
@@ -1628,7 +1643,7 @@ grb_probe_bench(grb_ctx* c, uint64_t filter_bits, double fill, uint32_t h, uint6
       best_i = std::min(best_i, ms);
     }
   }
-  c->launches += 2 * (uint64_t)(reps + 1);
+  c->launches += 3 * (uint64_t)(reps + 1);
   c->prof_free.push_back(e0);
   c->prof_free.push_back(e1);
   unsigned long long hsum[2] = { 0, 0 };
@@ -1637,6 +1652,8 @@ grb_probe_bench(grb_ctx* c, uint64_t filter_bits, double fill, uint32_t h, uint6
   GRB_CUDA(c, cudaGetLastError());
   out->query_ms = best_q;
   out->insert_ms = best_i;
+  out->line_query_ms = n_lines ? best_l : 0.0;
+  out->line_bytes = n_lines * 128;
   out->probes = n_keys * h;
   out->pop = pop;
   out->filter_bits = filter_bits;

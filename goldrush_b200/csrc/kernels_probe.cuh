@@ -120,3 +120,40 @@ k_probe_insert(GrbFilterDev filt, uint64_t n_keys, uint64_t n_fill, uint32_t h, 
     }
   }
 }
+
+// What a line-local filter layout could reach: one random 128-byte line per probe,
+// two dependent 16-byte reads inside it (header with bits + prefix, then the ID it selects).  `lines`
+// is any buffer of n_lines * 128 bytes; its content only feeds the checksum and the dependent offset.
+__global__ void __launch_bounds__(256)
+k_probe_line(const uint4* __restrict__ lines, uint64_t n_lines, uint64_t n_keys, uint32_t h,
+             uint64_t seed, uint64_t pick, unsigned long long* __restrict__ checksum)
+{
+  unsigned long long sum = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_keys;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = grb_splitmix64(pick + i);
+    uint4 head[GRB_MAX_PATTERNS];
+    uint64_t line[GRB_MAX_PATTERNS];
+#pragma unroll
+    for (uint32_t j = 0; j < GRB_MAX_PATTERNS; ++j) {
+      if (j < h) {
+        line[j] = __umul64hi(grb_splitmix64(seed + c * 8 + j), n_lines); // uniform in [0, n_lines)
+        head[j] = __ldg(&lines[line[j] * 8]);
+      }
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < GRB_MAX_PATTERNS; ++j) {
+      if (j < h) {
+        const uint4 id = __ldg(&lines[line[j] * 8 + 1 + (head[j].x + head[j].z) % 7]);
+        sum += id.y & 0xFFFFu;
+      }
+    }
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  }
+  if ((threadIdx.x & 31) == 0 && sum) {
+    atomicAdd(&checksum[0], sum);
+  }
+}
+

@@ -288,6 +288,10 @@ typedef struct grb_probe_bench_result
   uint64_t checksum;        /* sum of the IDs read by the query launches */
   uint64_t keys_filled;
   uint64_t probes_missed;   /* keys of the query launches that met a clear bit: must be 0 */
+  double line_query_ms;     /* the same probes as ONE random 128-byte line each (two dependent 16-byte
+                               reads inside it) over line_bytes of memory: what a line-local filter
+                               layout could reach */
+  uint64_t line_bytes;
 } grb_probe_bench_result;
 int grb_probe_bench(grb_ctx* ctx, uint64_t filter_bits, double fill, uint32_t h, uint64_t n_probes,
                     uint64_t seed, int reps, grb_probe_bench_result* out);

@@ -46,6 +46,9 @@ def main():
                 "query_gprobes_per_s": round(q / 1e9, 3), "insert_gprobes_per_s": round(i / 1e9, 3),
                 "query_algorithmic_gbs": round(q * 64 / 1e9, 1),    # 64 B per probe
                 "insert_algorithmic_gbs": round(i * 96 / 1e9, 1),   # 32 B block + 32 B slot read + 32 B write
+                "line_query_gprobes_per_s": round(r.probes / (r.line_query_ms * 1e-3) / 1e9, 3)
+                if r.line_query_ms > 0 else None,
+                "line_gb": round(r.line_bytes / 1e9, 3),
                 "checksum": r.checksum, "probes_missed": r.probes_missed}), flush=True)
             grb.lib().grb_release_cached_memory()
 
