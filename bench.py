@@ -453,6 +453,11 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    # torchrun exports OMP_NUM_THREADS=1; the synthetic read generator and the reference arm are
+    # OpenMP code: give every rank its share of the cores instead (before libgomp is loaded)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     if args.impl == "reference":
         bench_reference(args, w)
     else:
