@@ -16,19 +16,16 @@
 //   word 0      number of set bits in all earlier blocks (filled by grb_finalize_bitvector)
 //   words 1..3  192 filter bits, LSB first
 // so one probe (bit test + rank) touches exactly one sector.  The ID / count pair of the slot
-// with that rank (MIBloomFilter::m_data + MIBFConstructSupport::m_counts) is one 16-byte GrbSlot
-// {id, count, id0, epoch}: a query reads one more sector, an insert read-modify-writes one.
-// id0 / epoch are the engine's undo fields: the ID the slot held when batch `epoch` started, saved
-// by the first insert of that batch that rewrites the slot (kernels_batch.cuh).
+// with that rank (MIBloomFilter::m_data + MIBFConstructSupport::m_counts, 4 + 4 bytes per set bit,
+// MIBloomFilter.hpp:538-546, MIBFConstructSupport.hpp:336-339) is one 8-byte GrbSlot {id, count}:
+// a query reads its sector, an insert read-modify-writes it.
 // ---------------------------------------------------------------------------------------------
 #define GRB_BLK_BITS 192ull
 
-struct __align__(16) GrbSlot
+struct __align__(8) GrbSlot
 {
   uint32_t id;    // MIBloomFilter::m_data[rank] (bit 31 = saturation mask, MIBloomFilter.hpp:38)
   uint32_t count; // MIBFConstructSupport::m_counts[rank]
-  uint32_t id0;   // id at the start of the batch that last rewrote the slot
-  uint32_t epoch; // serial number of that batch (0 = never rewritten since the last ID reset)
 };
 
 struct GrbFilterDev

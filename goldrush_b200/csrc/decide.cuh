@@ -19,7 +19,7 @@
 
 // The smoothing code reads the per-tile votes through three accessors, so the same source serves
 // the candidate-list layout below and the dense count matrix of the batch engine
-// (kernels_batch.cuh: GrbMatrixVotes):
+// (batch_common.cuh: GrbMatrixVotes):
 //   best_id(i), best_count(i)   arg-max id of tile i (ties -> smallest id) and its count
 //   cand_count(i, id)           count of `id` in tile i if it is > 2 (a "candidate"), else 0
 struct GrbTileVotes

@@ -5,9 +5,9 @@
 #include "kernels_filter.cuh"
 #include "kernels_ntcard.cuh"
 #include "kernels_select.cuh"
-#include "kernels_batch.cuh"
-#include "kernels_batch2.cuh"
-#include "kernels_fix.cuh"
+#include "batch_common.cuh"
+#include "kernels_query.cuh"
+#include "kernels_commit.cuh"
 #include "comm.cuh"
 #include "kernels_probe.cuh"
 
@@ -246,42 +246,30 @@ struct grb_ctx
   DevBuf<uint64_t> b_tab_key, b_tab_mask;
   DevBuf<grb_decision> d_dec;
   size_t query_smem = 0, query2_smem = 0;
-  // batch engine (kernels_batch.cuh)
+  // batch engine (kernels_query.cuh + kernels_commit.cuh); GRB_ENGINE=serial keeps the
+  // one-read-at-a-time loop of kernels_select.cuh as the in-tree cross-check
   bool batch_mode = true;
   bool batch_reads_fixed = false; // GRB_BATCH_READS given: no adaptation to the genome size
   uint32_t batch_reads = 320;  // reads per speculative batch (A/B on B200: 64..800, profiles/README.md)
   uint32_t batch_tiles = 8192; // tile budget per batch (a single longer read still forms a batch)
-  uint32_t dirty_bits_log2 = 28;
-  uint64_t bt_cap = 0;         // capacity of the per-batch buffers, in tiles
   DevBuf<uint64_t> bb_stash;
-  DevBuf<uint32_t> bb_vt_n, bb_vt_id, bb_vt_cnt, bb_best_id, bb_best_count, bb_hits, bb_miss;
-  DevBuf<uint32_t> bb_dirty, bb_cmat, bb_uq, bb_nu, bb_uchg, bb_cm, bb_sp_id, bb_sp_nas, bb_inchg;
-  DevBuf<uint8_t> bb_sp_as;
+  DevBuf<uint32_t> bb_best_id, bb_best_count, bb_hits, bb_miss;
+  DevBuf<uint32_t> bb_uq, bb_nu, bb_cm, bb_sp_nas;
   DevBuf<GrbReadPlan> bb_sp_plan;
   DevBuf<uint32_t> bb_sp_adv, bb_rd_hits, bb_rd_miss, bb_rd_q;
-  DevBuf<uint64_t> bb_dd_key, bb_dd_mask;
-  DevBuf<uint64_t> bb_read_idx, bb_cm_off, bb_dd_off; // chunk descriptors
-  DevBuf<uint32_t> bb_dd_size;
+  DevBuf<uint64_t> bb_read_idx, bb_cm_off; // chunk descriptors
   DevBuf<uint32_t> bb_tile_first, bb_tile_read;
-  size_t check_smem = 0;
-  uint32_t fb_words = 0;
-  size_t commit_smem_max = 0;
-  uint32_t commit_ctas = 0;
-  DevBuf<unsigned long long> bb_barrier;
   DevBuf<uint64_t> bb_dec_idx;
-  // batch engine, second generation (kernels_batch2.cuh)
-  int batch_ver = 3; // GRB_ENGINE=batch1 / batch2 keep the earlier commit kernels for A/B runs
+  // per-batch query outputs and the probe index of the commit
   uint64_t b2_cap_tiles = 0, b2_ix_entries = 0;
   uint32_t b2_cap_reads = 0;
   bool b2_attr = false;
   size_t b2_smem_max = 0;
   DevBuf<uint32_t> b2_vk, b2_vc, b2_ix_sidx, b2_counters, b2_c_slot, b2_c_probe, b2_c_next, b2_c_sidx;
   DevBuf<unsigned long long> b2_ix;
-  DevBuf<GrbShared> b2_shared;
-  DevBuf<uint32_t> b2_fbits, b2_fl_n, b2_fl, b2_fr, b2_rl_n;
-  DevBuf<uint2> b2_rl;
+  DevBuf<uint32_t> b2_fbits, b2_fl_n, b2_fl, b2_fr;
   DevBuf<GrbReadPlan> b2_plan_out;
-  // third generation (kernels_fix.cuh); shares the b2_* probe-index buffers
+  // ordered commit (kernels_commit.cuh)
   bool b3_attr = false, b3_stage_attr = false;
   uint32_t b3_ctas = 0, b3_dcap = 0;
   uint64_t b3_cap_tiles = 0, b3_cmat_cap = 0;
@@ -613,7 +601,6 @@ grb_create(const grb_params* p, grb_ctx** out)
   // GRB_BATCH_READS overrides the speculative batch size
   if (const char* e = getenv("GRB_ENGINE")) {
     c->batch_mode = strcmp(e, "serial") != 0;
-    c->batch_ver = strcmp(e, "batch1") == 0 ? 1 : (strcmp(e, "batch2") == 0 ? 2 : 3);
   }
   if (const char* e = getenv("GRB_BATCH_TILES")) { // tile budget of a batch (26-bit probe index caps it)
     const long v = strtol(e, nullptr, 10);
@@ -1837,11 +1824,11 @@ sel_prepare(grb_ctx* c, uint64_t max_len)
     q.k = (uint32_t)k;
     q.h = (uint32_t)h;
     q.cand_cap = (uint32_t)(T * h / 3 + 1);
-    // A tile votes for at most T * h distinct ids.  The v3 engine never adds to the per-tile tables
+    // A tile votes for at most T * h distinct ids.  The batch engine never adds to the per-tile tables
     // after the query (its commit keeps deltas apart), so it needs no slack beyond a load factor
-    // below 3/4; the older engines re-vote into the tables and keep the 2x sizing.
+    // below 3/4; the serial engine keeps the 2x sizing.
     q.table_size = (uint32_t)next_pow2(2 * T * h);
-    if (c->batch_mode && c->batch_ver == 3) {
+    if (c->batch_mode) {
       const char* e = getenv("GRB_VOTE_TABLE");
       if (!(e && strcmp(e, "wide") == 0)) {
         q.table_size = (uint32_t)next_pow2(T * h + T * h / 3 + 1);
@@ -1928,8 +1915,7 @@ launch_read(grb_ctx* c, uint64_t r, uint64_t dec_idx, grb_decision* d_dec)
     c->kbegin();
     k_insert_collect<<<cgrid, 256, 0, s>>>(c->reads_dev(), c->prm, c->sc, c->sc.stash, c->d_state,
                                            r, (uint32_t)round, tab);
-    k_insert_apply<<<agrid, 256, 0, s>>>(c->filt, c->sc, c->d_state, r, (uint32_t)round, tab,
-                                         nullptr, 0u);
+    k_insert_apply<<<agrid, 256, 0, s>>>(c->filt, c->sc, c->d_state, r, (uint32_t)round, tab);
     c->kend(GRB_K_INSERT, 2);
   }
 }
@@ -1942,194 +1928,16 @@ struct BatchPlan
   std::vector<uint32_t> tile_first; // per batch: local prefix (nb + 1 entries each), concatenated
   std::vector<uint32_t> tile_read;  // per batch: b of each tile, concatenated
   std::vector<uint64_t> cm_off;     // per read: offset of its count matrix within the batch
-  std::vector<uint64_t> dd_off;     // per read: offset / size of its de-duplication table
-  std::vector<uint32_t> dd_size;
   struct Batch
   {
     uint32_t read0, nb, tf0, tr0, n_bt;
     uint32_t max_tiles; // longest read of the batch, in tiles
     uint64_t cm_words;  // sum of tiles^2
-    uint64_t dd_entries;
   };
   std::vector<Batch> batches;
 };
 
-static int
-batch_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, uint64_t max_cm_words,
-              uint64_t max_dd_entries)
-{
-  cudaStream_t s = c->stream;
-  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
-  if (max_batch_tiles > c->bt_cap) {
-    const uint64_t n = max_batch_tiles;
-    const uint64_t cap = T * h;
-    c->bb_stash.release();
-    c->bb_vt_id.release();
-    c->bb_vt_cnt.release();
-    GRB_CUDA(c, c->bb_stash.reserve(n * T * h, 0, s));
-    GRB_CUDA(c, c->bb_vt_id.reserve(n * cap, 0, s));
-    GRB_CUDA(c, c->bb_vt_cnt.reserve(n * cap, 0, s));
-    GRB_CUDA(c, c->bb_vt_n.reserve(n, 0, s));
-    GRB_CUDA(c, c->bb_best_id.reserve(n, 0, s));
-    GRB_CUDA(c, c->bb_best_count.reserve(n, 0, s));
-    GRB_CUDA(c, c->bb_hits.reserve(n, 0, s));
-    GRB_CUDA(c, c->bb_miss.reserve(n, 0, s));
-    GRB_CUDA(c, c->bb_uq.reserve(n, 0, s));
-    GRB_CUDA(c, c->bb_sp_id.reserve(n, 0, s));
-    GRB_CUDA(c, c->bb_sp_as.reserve(n, 0, s));
-    c->bt_cap = n;
-  }
-  GRB_CUDA(c, c->bb_sp_nas.reserve(c->batch_reads, 0, s));
-  GRB_CUDA(c, c->bb_inchg.reserve(c->batch_reads, 0, s));
-  GRB_CUDA(c, c->bb_sp_plan.reserve(c->batch_reads, 0, s));
-  GRB_CUDA(c, c->bb_sp_adv.reserve(c->batch_reads, 0, s));
-  GRB_CUDA(c, c->bb_rd_hits.reserve(c->batch_reads, 0, s));
-  GRB_CUDA(c, c->bb_rd_miss.reserve(c->batch_reads, 0, s));
-  GRB_CUDA(c, c->bb_rd_q.reserve(c->batch_reads, 0, s));
-  if (max_dd_entries > c->bb_dd_key.cap) {
-    c->bb_dd_key.release();
-    c->bb_dd_mask.release();
-    GRB_CUDA(c, c->bb_dd_key.reserve(max_dd_entries, 0, s));
-    GRB_CUDA(c, c->bb_dd_mask.reserve(max_dd_entries, 0, s));
-  }
-  GRB_CUDA(c, c->bb_nu.reserve(c->batch_reads, 0, s));
-  GRB_CUDA(c, c->bb_uchg.reserve(c->batch_reads, 0, s));
-  GRB_CUDA(c, c->bb_cm.reserve(std::max<uint64_t>(1, max_cm_words), 0, s));
-  if (max_read_tiles > 2048) {
-    return c->fail(GRB_ERR_ARG, "a read spans more than 2048 tiles: raise the tile length");
-  }
-  GRB_CUDA(c, c->bb_dirty.reserve((1ull << c->dirty_bits_log2) / 32, 0, s));
-  if (max_read_tiles > 160) { // count matrix of a very long read spills to global memory
-    GRB_CUDA(c, c->bb_cmat.reserve(max_read_tiles * max_read_tiles, 0, s));
-  }
-  if (c->check_smem == 0) {
-    c->fb_words = (uint32_t)((T + 31) / 32 + 1);
-    c->check_smem = (size_t)c->fb_words * 4 + (size_t)c->prm.table_size * 8;
-    int max_optin = 0;
-    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
-    c->commit_smem_max = (size_t)max_optin - 2048; // static shared memory of the kernel
-    GRB_CUDA(c, cudaFuncSetAttribute(k_commit_batch<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)c->commit_smem_max));
-    int per_sm = 0;
-    GRB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_commit_batch<1024>, 1024,
-                                                              c->commit_smem_max));
-    if (per_sm < 1) {
-      return c->fail(GRB_ERR_CUDA, "k_commit_batch cannot be resident on this device");
-    }
-    c->commit_ctas = (uint32_t)c->sm_count;
-    GRB_CUDA(c, c->bb_barrier.reserve(1, 0, s));
-    GRB_CUDA(c, cudaFuncSetAttribute(k_spec_cmat<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     200 * 1024));
-    GRB_CUDA(c, cudaFuncSetAttribute(k_spec_query<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)c->query_smem));
-  }
-  return GRB_OK;
-}
-
-static GrbBatchDev
-batch_dev(grb_ctx* c, const BatchPlan::Batch& b)
-{
-  GrbBatchDev d{};
-  d.read_idx = c->bb_read_idx.p + b.read0;
-  d.tile_first = c->bb_tile_first.p + b.tf0;
-  d.tile_read = c->bb_tile_read.p + b.tr0;
-  d.nb = b.nb;
-  d.n_bt = b.n_bt;
-  d.stash = c->bb_stash.p;
-  d.vt_n = c->bb_vt_n.p;
-  d.vt_id = c->bb_vt_id.p;
-  d.vt_cnt = c->bb_vt_cnt.p;
-  d.best_id = c->bb_best_id.p;
-  d.best_count = c->bb_best_count.p;
-  d.tile_hits = c->bb_hits.p;
-  d.tile_miss = c->bb_miss.p;
-  d.vt_cap = (uint32_t)(c->p.tile_length * c->h_seed.h);
-  d.dirty_mask = (uint32_t)((1ull << c->dirty_bits_log2) - 1);
-  d.dirty_bits = c->bb_dirty.p;
-  d.cmat = c->bb_cmat.p;
-  d.uq = c->bb_uq.p;
-  d.nu = c->bb_nu.p;
-  d.u_changed = c->bb_uchg.p;
-  d.cm = c->bb_cm.p;
-  d.cm_off = c->bb_cm_off.p + b.read0;
-  d.sp_tile_id = c->bb_sp_id.p;
-  d.sp_tile_as = c->bb_sp_as.p;
-  d.sp_n_as = c->bb_sp_nas.p;
-  d.in_changed = c->bb_inchg.p;
-  d.sp_plan = c->bb_sp_plan.p;
-  d.sp_adv = c->bb_sp_adv.p;
-  d.rd_hits = c->bb_rd_hits.p;
-  d.rd_miss = c->bb_rd_miss.p;
-  d.rd_queries = c->bb_rd_q.p;
-  d.dd_key = c->bb_dd_key.p;
-  d.dd_mask = c->bb_dd_mask.p;
-  d.dd_off = c->bb_dd_off.p + b.read0;
-  d.dd_size = c->bb_dd_size.p + b.read0;
-  return d;
-}
-
-// speculative query of one batch, then the ordered commit of its reads
-static int
-launch_batch(grb_ctx* c, const BatchPlan& bp, const BatchPlan::Batch& b, uint64_t first,
-             grb_decision* d_dec)
-{
-  cudaStream_t s = c->stream;
-  const GrbBatchDev bd = batch_dev(c, b);
-  GRB_CUDA(c, cudaMemsetAsync(c->bb_dirty.p, 0, (1ull << c->dirty_bits_log2) / 8, s));
-  k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
-  c->launches += 1;
-  c->kbegin();
-  k_spec_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query_smem, s>>>(
-    c->reads_dev(), c->d_seed, c->filt, c->prm, bd, c->d_state);
-  c->kend(GRB_K_QUERY);
-  c->kbegin();
-  {
-    const uint32_t n_cap = std::max<uint32_t>(b.max_tiles, 1);
-    const uint32_t us = (uint32_t)next_pow2(2 * (uint64_t)n_cap);
-    k_spec_cmat<256><<<b.nb, 256, (size_t)(5 * n_cap + 2 + 2 * us) * 4 + n_cap, s>>>(
-      c->reads_dev(), c->prm, bd, c->d_state, n_cap, us);
-  }
-  c->kend(GRB_K_SMOOTH);
-  if (b.dd_entries) {
-    GRB_CUDA(c, cudaMemsetAsync(c->bb_dd_key.p, 0xFF, b.dd_entries * 8, s));
-    GRB_CUDA(c, cudaMemsetAsync(c->bb_dd_mask.p, 0, b.dd_entries * 8, s));
-    c->kbegin();
-    k_spec_dedupe<<<grid_for(b.n_bt, 1, 1u << 20), 256, 0, s>>>(c->reads_dev(), c->prm, bd,
-                                                               c->d_state);
-    c->kend(GRB_K_DEDUPE);
-  }
-  // ---- ordered commit: one persistent cooperative launch ----
-  {
-    const uint32_t n_cap = std::max<uint32_t>(b.max_tiles, 1);
-    const uint32_t us = (uint32_t)next_pow2(2 * (uint64_t)n_cap);
-    uint32_t cm_smem = n_cap <= 160 ? 1u : 0u;
-    size_t smem = ((size_t)c->fb_words + 2 * (size_t)c->prm.table_size + 3 * (size_t)us +
-                   6 * (size_t)n_cap + 2) * 4 + ((n_cap + 15) / 16) * 16 +
-                  (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
-    if (smem > c->commit_smem_max) {
-      return c->fail(GRB_ERR_ARG, "a read spans too many tiles for the commit kernel's shared "
-                                  "memory: raise the tile length");
-    }
-    GRB_CUDA(c, cudaMemsetAsync(c->bb_barrier.p, 0, 8, s));
-    GrbReadsDev reads = c->reads_dev();
-    GrbBatchDev bdv = bd;
-    GrbSelState* st = c->d_state;
-    grb_decision* dec = d_dec;
-    const uint64_t* dec_idx = c->bb_dec_idx.p + b.read0;
-    unsigned long long* ctr = c->bb_barrier.p;
-    uint32_t fbw = c->fb_words, us_a = us, n_cap_a = n_cap;
-    void* args[] = { &reads, &c->filt, &c->prm, &bdv, &c->sc, &st, &dec, &dec_idx, &ctr,
-                     &fbw,   &us_a,    &n_cap_a, &cm_smem };
-    c->kbegin();
-    GRB_CUDA(c, cudaLaunchCooperativeKernel((void*)k_commit_batch<1024>, dim3(c->commit_ctas),
-                                            dim3(1024), args, smem, s));
-    c->kend(GRB_K_COMMIT);
-  }
-  GRB_CUDA(c, cudaGetLastError());
-  return GRB_OK;
-}
-
-// ---- batch engine, second generation ------------------------------------------------------
+// ---- batch engine: query-side buffers ------------------------------------------------------
 static int
 batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, uint64_t max_cm_words,
                uint32_t max_batch_reads)
@@ -2160,11 +1968,9 @@ batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
     GRB_CUDA(c, c->b2_c_probe.reserve(n_probe, 0, s));
     GRB_CUDA(c, c->b2_c_next.reserve(n_probe, 0, s));
     GRB_CUDA(c, c->b2_c_sidx.reserve(n_probe, 0, s));
-    GRB_CUDA(c, c->b2_shared.reserve(n_probe / 2 + 1, 0, s));
     GRB_CUDA(c, c->b2_fbits.reserve(n * T / 32 + 2, 0, s));
     GRB_CUDA(c, c->b2_fl.reserve(n * T, 0, s));
     GRB_CUDA(c, c->b2_fr.reserve(n * T * (2 + h), 0, s));
-    GRB_CUDA(c, c->b2_rl.reserve(n_probe, 0, s));
     GRB_CUDA(c, c->bb_best_id.reserve(n, 0, s));
     GRB_CUDA(c, c->bb_best_count.reserve(n, 0, s));
     GRB_CUDA(c, c->bb_hits.reserve(n, 0, s));
@@ -2183,20 +1989,14 @@ batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
     GRB_CUDA(c, c->bb_rd_q.reserve(nb, 0, s));
     GRB_CUDA(c, c->bb_nu.reserve(nb, 0, s));
     GRB_CUDA(c, c->b2_fl_n.reserve(nb, 0, s));
-    GRB_CUDA(c, c->b2_rl_n.reserve(nb, 0, s));
     GRB_CUDA(c, c->b2_plan_out.reserve(nb, 0, s));
     c->b2_cap_reads = nb;
   }
   GRB_CUDA(c, c->bb_cm.reserve(std::max<uint64_t>(1, max_cm_words), 0, s));
-  if (max_read_tiles > 160) { // count matrix of a very long read spills to global memory
-    GRB_CUDA(c, c->bb_cmat.reserve(max_read_tiles * max_read_tiles, 0, s));
-  }
   if (!c->b2_attr) {
     int max_optin = 0;
     cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
     c->b2_smem_max = (size_t)max_optin - 2048; // static shared memory of the kernels
-    GRB_CUDA(c, cudaFuncSetAttribute(k2_commit<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)c->b2_smem_max));
     GRB_CUDA(c, cudaFuncSetAttribute(k2_cmat<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)c->b2_smem_max));
     c->query2_smem = (size_t)c->gt_groups * 256 * 32 + (size_t)c->prm.sw_words * 8 +
@@ -2211,103 +2011,7 @@ batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
   return GRB_OK;
 }
 
-static int
-launch_batch2(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
-{
-  cudaStream_t s = c->stream;
-  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
-  GrbBatchDev bd{};
-  bd.read_idx = c->bb_read_idx.p + b.read0;
-  bd.tile_first = c->bb_tile_first.p + b.tf0;
-  bd.tile_read = c->bb_tile_read.p + b.tr0;
-  bd.nb = b.nb;
-  bd.n_bt = b.n_bt;
-  bd.stash = c->bb_stash.p;
-  bd.best_id = c->bb_best_id.p;
-  bd.best_count = c->bb_best_count.p;
-  bd.tile_hits = c->bb_hits.p;
-  bd.tile_miss = c->bb_miss.p;
-  bd.cmat = c->bb_cmat.p;
-  bd.uq = c->bb_uq.p;
-  bd.nu = c->bb_nu.p;
-  bd.cm = c->bb_cm.p;
-  bd.cm_off = c->bb_cm_off.p + b.read0;
-  bd.sp_n_as = c->bb_sp_nas.p;
-  bd.sp_plan = c->bb_sp_plan.p;
-  bd.sp_adv = c->bb_sp_adv.p;
-  bd.rd_hits = c->bb_rd_hits.p;
-  bd.rd_miss = c->bb_rd_miss.p;
-  bd.rd_queries = c->bb_rd_q.p;
-  GrbB2 b2{};
-  b2.vk = c->b2_vk.p;
-  b2.vc = c->b2_vc.p;
-  b2.table_size = c->prm.table_size;
-  b2.ix_tab = c->b2_ix.p;
-  const uint64_t n_probe = (uint64_t)b.n_bt * T * h;
-  const uint64_t ix_entries = std::min<uint64_t>(c->b2_ix_entries, next_pow2(n_probe + n_probe / 2 + 64));
-  b2.ix_mask = ix_entries - 1;
-  b2.ix_sidx = c->b2_ix_sidx.p;
-  b2.counters = c->b2_counters.p;
-  b2.c_slot = c->b2_c_slot.p;
-  b2.c_probe = c->b2_c_probe.p;
-  b2.c_next = c->b2_c_next.p;
-  b2.c_sidx = c->b2_c_sidx.p;
-  b2.shared = c->b2_shared.p;
-  b2.fbits = c->b2_fbits.p;
-  b2.fl_n = c->b2_fl_n.p;
-  b2.fl = c->b2_fl.p;
-  b2.fr = c->b2_fr.p;
-  b2.rl_n = c->b2_rl_n.p;
-  b2.rl = c->b2_rl.p;
-  b2.plan_out = c->b2_plan_out.p;
-
-  const uint32_t n_cap = std::max<uint32_t>(b.max_tiles, 1);
-  const uint32_t us = (uint32_t)next_pow2(2 * (uint64_t)n_cap);
-  const uint32_t cm_smem = n_cap <= 160 ? 1u : 0u;
-  const size_t as_pad = ((size_t)(n_cap + 15) / 16) * 16;
-  const size_t cmat_smem = (size_t)6 * n_cap * 4 + 8 + (size_t)2 * us * 4 + as_pad +
-                           (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
-  const size_t commit_smem = (size_t)n_cap * 8 + ((size_t)2 * us + (size_t)8 * n_cap + 2) * 4 + as_pad +
-                             (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
-  if (cmat_smem > c->b2_smem_max || commit_smem > c->b2_smem_max) {
-    return c->fail(GRB_ERR_ARG, "a read spans too many tiles for the commit kernel's shared "
-                                "memory: raise the tile length");
-  }
-  GRB_CUDA(c, cudaMemsetAsync(b2.ix_tab, 0xFF, ix_entries * 8, s));
-  GRB_CUDA(c, cudaMemsetAsync(b2.fbits, 0, ((uint64_t)b.n_bt * T / 32 + 2) * 4, s));
-  GRB_CUDA(c, cudaMemsetAsync(b2.counters, 0, 16, s));
-  GRB_CUDA(c, cudaMemsetAsync(b2.fl_n, 0, (size_t)b.nb * 4, s));
-  GRB_CUDA(c, cudaMemsetAsync(b2.rl_n, 0, (size_t)b.nb * 4, s));
-  GRB_CUDA(c, cudaMemsetAsync(b2.plan_out, 0, (size_t)b.nb * sizeof(GrbReadPlan), s));
-  k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
-  c->launches += 1;
-  c->kbegin();
-  k2_query<512><<<grid_for(b.n_bt, 1, 1u << 20), 512, c->query2_smem, s>>>(
-    c->reads_dev(), c->d_seed, c->d_gtab, c->gt_groups, c->filt, c->prm, bd, b2, c->d_state, 0u, b.n_bt);
-  c->kend(GRB_K_QUERY);
-  c->kbegin();
-  k2_cmat<256><<<b.nb, 256, cmat_smem, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state, n_cap, us,
-                                           cm_smem);
-  c->kend(GRB_K_SMOOTH);
-  c->kbegin();
-  k2_index<<<grid_for(b.n_bt, 1, 1u << 20), 256, 0, s>>>(c->reads_dev(), c->filt, c->prm, bd, b2,
-                                                         c->d_state);
-  k2_conf<<<c->sm_count * 8, 256, 0, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state);
-  k2_conf2<<<c->sm_count * 8, 256, 0, s>>>(c->reads_dev(), c->filt, c->prm, bd, b2, c->d_state);
-  c->kend(GRB_K_DEDUPE, 3);
-  c->kbegin();
-  k2_commit<1024><<<1, 1024, commit_smem, s>>>(c->reads_dev(), c->prm, bd, b2, c->d_state, d_dec,
-                                               c->bb_dec_idx.p + b.read0, us, n_cap, cm_smem);
-  c->kend(GRB_K_COMMIT);
-  c->kbegin();
-  k2_bulk<<<grid_for(b.n_bt, 1, c->sm_count * 16), 256, 0, s>>>(c->reads_dev(), c->filt, c->prm, bd,
-                                                                b2, c->d_state);
-  c->kend(GRB_K_INSERT);
-  GRB_CUDA(c, cudaGetLastError());
-  return GRB_OK;
-}
-
-// ---- batch engine, third generation -------------------------------------------------------
+// ---- batch engine: commit-side buffers and the per-batch launch sequence -------------------
 static const uint32_t kFixDeltaSmem = 8192; // shared-memory delta table entries of k3_fix
 
 static int
@@ -2385,7 +2089,6 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   bd.best_count = c->bb_best_count.p;
   bd.tile_hits = c->bb_hits.p;
   bd.tile_miss = c->bb_miss.p;
-  bd.cmat = c->bb_cmat.p;
   bd.uq = c->bb_uq.p;
   bd.nu = c->bb_nu.p;
   bd.cm = c->bb_cm.p;
@@ -2601,13 +2304,11 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       // cut the next kChunk visited reads into batches and describe them to the device
       BatchPlan bp;
       const uint64_t T = c->p.tile_length;
-      uint64_t max_bt = 0, max_cm = 0, max_dd = 0;
+      uint64_t max_bt = 0, max_cm = 0;
       uint32_t max_nb = 0;
-      // the second-generation engine indexes a batch's probes with 26 bits
-      const uint64_t tile_budget =
-        c->batch_ver >= 2 ? std::max<uint64_t>(1, std::min<uint64_t>(c->batch_tiles,
-                                                                     ((1ull << 26) - 1) / (T * c->h_seed.h)))
-                          : c->batch_tiles;
+      // the commit indexes a batch's probes with 26 bits
+      const uint64_t tile_budget = std::max<uint64_t>(
+        1, std::min<uint64_t>(c->batch_tiles, ((1ull << 26) - 1) / (T * c->h_seed.h)));
       for (; j < end && launched < kChunk; ++j) {
         if (!(c->h_flags[j] & GRB_READ_PASS2)) {
           continue;
@@ -2620,19 +2321,12 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
           }
           bp.batches.push_back(BatchPlan::Batch{ (uint32_t)bp.read_idx.size(), 0,
                                                  (uint32_t)bp.tile_first.size(),
-                                                 (uint32_t)bp.tile_read.size(), 0, 0, 0, 0 });
+                                                 (uint32_t)bp.tile_read.size(), 0, 0, 0 });
         }
         BatchPlan::Batch& b = bp.batches.back();
         bp.read_idx.push_back(j);
         bp.dec_idx.push_back(j - first);
         bp.cm_off.push_back(b.cm_words);
-        bp.dd_off.push_back(b.dd_entries);
-        const uint64_t dd = (c->batch_ver == 1 && tiles >= 1 && tiles <= 64)
-                              ? next_pow2(2ull * tiles * T * c->h_seed.h)
-                              : 0;
-        bp.dd_size.push_back((uint32_t)dd);
-        b.dd_entries += dd;
-        max_dd = std::max(max_dd, b.dd_entries);
         b.cm_words += (uint64_t)tiles * tiles;
         b.max_tiles = std::max(b.max_tiles, tiles);
         max_cm = std::max(max_cm, b.cm_words);
@@ -2648,11 +2342,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
         bp.tile_first.push_back(bp.batches.back().n_bt);
         // with W ranks every per-tile buffer holds W equal shares (the last one padded)
         const uint64_t pad_bt = (c->comm && c->shard_query) ? (uint64_t)c->comm->world : 0;
-        rc = c->batch_ver == 3
-               ? batch3_prepare(c, std::max<uint64_t>(max_bt, 1) + pad_bt, max_len / T, max_cm, max_nb)
-               : c->batch_ver == 2
-                   ? batch2_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_nb)
-                   : batch_prepare(c, std::max<uint64_t>(max_bt, 1), max_len / T, max_cm, max_dd);
+        rc = batch3_prepare(c, std::max<uint64_t>(max_bt, 1) + pad_bt, max_len / T, max_cm, max_nb);
         if (rc != GRB_OK) {
           return rc;
         }
@@ -2664,12 +2354,6 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
         GRB_CUDA(c, c->bb_dec_idx.reserve(bp.dec_idx.size(), 0, s));
         GRB_CUDA(c, cudaMemcpyAsync(c->bb_dec_idx.p, bp.dec_idx.data(), bp.dec_idx.size() * 8,
                                     cudaMemcpyHostToDevice, s));
-        GRB_CUDA(c, c->bb_dd_off.reserve(bp.dd_off.size(), 0, s));
-        GRB_CUDA(c, c->bb_dd_size.reserve(bp.dd_size.size(), 0, s));
-        GRB_CUDA(c, cudaMemcpyAsync(c->bb_dd_off.p, bp.dd_off.data(), bp.dd_off.size() * 8,
-                                    cudaMemcpyHostToDevice, s));
-        GRB_CUDA(c, cudaMemcpyAsync(c->bb_dd_size.p, bp.dd_size.data(), bp.dd_size.size() * 4,
-                                    cudaMemcpyHostToDevice, s));
         GRB_CUDA(c, c->bb_cm_off.reserve(bp.cm_off.size(), 0, s));
         GRB_CUDA(c, cudaMemcpyAsync(c->bb_cm_off.p, bp.cm_off.data(), bp.cm_off.size() * 8,
                                     cudaMemcpyHostToDevice, s));
@@ -2680,9 +2364,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
                                       bp.tile_read.size() * 4, cudaMemcpyHostToDevice, s));
         }
         for (const BatchPlan::Batch& b : bp.batches) {
-          rc = c->batch_ver == 3 ? launch_batch3(c, b, c->d_dec.p)
-               : c->batch_ver == 2 ? launch_batch2(c, b, c->d_dec.p)
-                                   : launch_batch(c, bp, b, first, c->d_dec.p);
+          rc = launch_batch3(c, b, c->d_dec.p);
           if (rc != GRB_OK) {
             return rc;
           }
@@ -2895,7 +2577,7 @@ grb_insert_tiles(grb_ctx* c, uint64_t read_idx, uint32_t tile_start, uint32_t ti
   k_insert_collect<<<grid_for(n, 256, c->sm_count * 4), 256, 0, s>>>(
     c->reads_dev(), q, sc, sc.stash, tmp.p, read_idx, 0, (uint32_t)tab);
   k_insert_apply<<<grid_for(tab, 256, c->sm_count * 4), 256, 0, s>>>(
-    c->filt, sc, tmp.p, read_idx, 0, (uint32_t)tab, nullptr, 0u);
+    c->filt, sc, tmp.p, read_idx, 0, (uint32_t)tab);
   c->launches += 3;
   GRB_CUDA(c, cudaStreamSynchronize(s));
   GRB_CUDA(c, cudaGetLastError());

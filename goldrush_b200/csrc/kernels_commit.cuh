@@ -5,7 +5,7 @@
 // MIBFConstructSupport.hpp:247-283 insertMIBF) and produces the same decisions: every query sees
 // every earlier insert (goldrush_path.cpp:1229-1256), exactly.
 //
-// As in kernels_batch2.cuh a rank probed by one valid probe of the batch is private (its reservoir
+// A rank probed by one valid probe of the batch is private (its reservoir
 // update is applied after the commit, k3_bulk) and a rank probed twice or more is shared.  The
 // members (probes) of a shared rank are sorted by (read, tile).  Given a PLAN for every read of the
 // batch (insert or not, tile range, ids), the history of every shared rank follows by walking its
@@ -23,7 +23,8 @@
 #include "common.cuh"
 #include "decide.cuh"
 #include "kernels_select.cuh"
-#include "kernels_batch2.cuh"
+#include "batch_common.cuh"
+#include "kernels_query.cuh"
 
 struct __align__(16) GrbShared3
 {

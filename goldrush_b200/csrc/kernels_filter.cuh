@@ -456,7 +456,7 @@ k_set_slots(GrbSlot* __restrict__ slots, const uint64_t* __restrict__ rank, uint
 {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    slots[rank[i]] = GrbSlot{ ids[i], counts[i], ids[i], 0u };
+    slots[rank[i]] = GrbSlot{ ids[i], counts[i] };
   }
 }
 

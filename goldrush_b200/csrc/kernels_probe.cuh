@@ -11,7 +11,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_filter.cuh"
-#include "kernels_batch2.cuh"
+#include "batch_common.cuh"
 
 __host__ __device__ __forceinline__ uint64_t
 grb_splitmix64(uint64_t x)
@@ -41,7 +41,7 @@ k_probe_ids(GrbSlot* __restrict__ slots, uint64_t pop, uint64_t seed)
        r += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t m = grb_splitmix64(seed ^ r);
     const uint32_t id = (m & 1) ? (uint32_t)((m >> 8) & 0x00FFFFFFu) | 1u : 0u;
-    slots[r] = GrbSlot{ id, id ? 1u : 0u, id, 0u };
+    slots[r] = GrbSlot{ id, id ? 1u : 0u };
   }
 }
 

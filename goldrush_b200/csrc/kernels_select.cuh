@@ -27,7 +27,7 @@ struct GrbSelParams
 
 struct GrbSelState
 {
-  uint32_t epoch;         // serial number of the current batch (kernels_batch.cuh), never 0
+  uint32_t pad0;
   uint32_t batch_inserts; // reads of the current batch that inserted so far
   uint32_t ids_inserted;
   uint32_t halt;     // set at a path rollover: later kernels are no-ops until the host resumes
@@ -373,8 +373,7 @@ k_insert_collect(GrbReadsDev reads, GrbSelParams prm, GrbSelScratch sc,
 // (MIBFConstructSupport.hpp:271-282, MIBloomFilter.hpp:593-602), then clears the table entry.
 __global__ void __launch_bounds__(256)
 k_insert_apply(GrbFilterDev filt, GrbSelScratch sc, const GrbSelState* __restrict__ state,
-               uint64_t read_idx, uint32_t round, uint32_t tab_size, uint32_t* __restrict__ dirty_bits,
-               uint32_t dirty_mask)
+               uint64_t read_idx, uint32_t round, uint32_t tab_size)
 {
   const GrbReadPlan plan = *sc.plan;
   if (plan.n_blocks <= 64 * round || (plan.verdict != GRB_UNTRIMMED && plan.verdict != GRB_TRIMMED)) {
@@ -391,7 +390,6 @@ k_insert_apply(GrbFilterDev filt, GrbSelScratch sc, const GrbSelState* __restric
     }
     uint64_t m = sc.tab_mask[i];
     GrbSlot s = filt.slots[key];
-    const uint32_t orig = s.id;
     while (m) {
       const uint32_t j = __ffsll((long long)m) - 1;
       m &= m - 1;
@@ -400,17 +398,6 @@ k_insert_apply(GrbFilterDev filt, GrbSelScratch sc, const GrbSelState* __restric
       if ((uint32_t)(key ^ (uint64_t)id) % count == count - 1) {
         s.id = s.id > GRB_SAT_MASK ? (id | GRB_SAT_MASK) : id;
       }
-    }
-    if (dirty_bits && s.id != orig) {
-      // batch engine: remember the ID the slot held when the batch started (unless an earlier
-      // read of this batch already rewrote it) and flag the slot for the later reads' re-validation
-      const uint32_t epoch = state->epoch;
-      if (s.epoch != epoch) {
-        s.id0 = orig;
-        s.epoch = epoch;
-      }
-      const uint32_t hb = (uint32_t)key & dirty_mask;
-      atomicOr(&dirty_bits[hb >> 5], 1u << (hb & 31));
     }
     filt.slots[key] = s;
     sc.tab_key[i] = GRB_EMPTY_KEY;

@@ -461,7 +461,7 @@ def test_batch_engine_equals_serial_engine(shape):
     ref = _select_all(data, {"GRB_ENGINE": "serial"}, **dict(params))
     assert any(d[0] in (2, 3) for d in ref[0]) and any(d[0] == 4 for d in ref[0])
     for eng, b in (("batch", "1"), ("batch", "3"), ("batch", "32"), ("batch", "128"),
-                   ("batch", "512"), ("batch2", "32")):
+                   ("batch", "512")):
         got = _select_all(data, {"GRB_ENGINE": eng, "GRB_BATCH_READS": b}, **dict(params))
         assert got[0] == ref[0], b
         assert got[1] == ref[1], b
