@@ -23,7 +23,7 @@ struct GrbBatchDev
   const uint32_t* tile_first; // [nb + 1] first batch tile of read b
   const uint32_t* tile_read;  // [n_bt] b of each batch tile
   uint32_t nb, n_bt;
-  uint64_t* stash;      // [n_bt * tile_len * h] rank of every probe
+  uint64_t* stash;      // [n_bt * tile_frames * h] rank of every probe
   uint32_t* best_id;    // [n_bt]
   uint32_t* best_count; // [n_bt]
   uint32_t* tile_hits;  // [n_bt]
@@ -201,14 +201,14 @@ grb2_probe_at(const GrbReadsDev& reads, const GrbSelParams& prm, const GrbBatchD
 {
   GrbProbeAt a;
   const uint32_t T = prm.tile_len, h = prm.h, k = prm.k;
-  const uint32_t per_tile = T * h;
+  const uint32_t per_tile = prm.tile_frames * h;
   a.bt = idx / per_tile;
   const uint32_t rem = idx - a.bt * per_tile;
   a.f = rem / h;
   a.p = rem - a.f * h;
   a.b = bd.tile_read[a.bt];
   a.t = a.bt - bd.tile_first[a.b];
-  a.tl = grb_tile_bases(reads.len[bd.read_idx[a.b]], a.t, T, k);
+  a.tl = grb_tile_bases(reads.len[bd.read_idx[a.b]], a.t, T, prm.kmer);
   a.valid = a.tl >= k + a.p && a.f < a.tl - (k + a.p) + 1;
   return a;
 }

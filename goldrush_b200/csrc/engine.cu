@@ -181,6 +181,7 @@ struct grb_ctx
   double last_ms = 0;
   uint64_t launches = 0;
   int sm_count = 148;
+  uint64_t tile_frames = 0; // frames of a full tile: tile_length + kmer_size - span of pattern 0
 
   GrbSeedTables h_seed{};
   GrbSeedTables* d_seed = nullptr;
@@ -566,6 +567,15 @@ grb_create(const grb_params* p, grb_ctx** out)
   if (p->tile_length < c->h_seed.k + c->h_seed.h - 1) {
     return bail(GRB_ERR_ARG, "grb_create: tile_length shorter than the longest seed span");
   }
+  // make_seed_pattern builds pattern 0 from two halves of k / 2 positions (spaced_seeds.cpp:28,
+  // 58-60): its span is k - 1 for an odd -k, and the reference then dies on
+  // assert(m_sseeds[0].size() == kmerSize) (MIBloomFilter.hpp:180) once pass 1 is done.  Refused
+  // here, before any work.
+  if (p->kmer_size != c->h_seed.k) {
+    return bail(GRB_ERR_ARG, "grb_create: seed pattern 0 must span kmer_size (an odd -k gives seeds "
+                             "of span k - 1, which the reference rejects: MIBloomFilter.hpp:180)");
+  }
+  c->tile_frames = p->tile_length + p->kmer_size - c->h_seed.k;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -1818,20 +1828,23 @@ sel_prepare(grb_ctx* c, uint64_t max_len)
 {
   cudaStream_t s = c->stream;
   const uint64_t T = c->p.tile_length, h = c->h_seed.h, k = c->h_seed.k;
+  const uint64_t F = c->tile_frames;
   if (!c->sel_init) {
     GrbSelParams& q = c->prm;
     q.tile_len = (uint32_t)T;
+    q.kmer = (uint32_t)c->p.kmer_size;
+    q.tile_frames = (uint32_t)F;
     q.k = (uint32_t)k;
     q.h = (uint32_t)h;
-    q.cand_cap = (uint32_t)(T * h / 3 + 1);
-    // A tile votes for at most T * h distinct ids.  The batch engine never adds to the per-tile tables
+    q.cand_cap = (uint32_t)(F * h / 3 + 1);
+    // A tile votes for at most F * h distinct ids.  The batch engine never adds to the per-tile tables
     // after the query (its commit keeps deltas apart), so it needs no slack beyond a load factor
     // below 3/4; the serial engine keeps the 2x sizing.
-    q.table_size = (uint32_t)next_pow2(2 * T * h);
+    q.table_size = (uint32_t)next_pow2(2 * F * h);
     if (c->batch_mode) {
       const char* e = getenv("GRB_VOTE_TABLE");
       if (!(e && strcmp(e, "wide") == 0)) {
-        q.table_size = (uint32_t)next_pow2(T * h + T * h / 3 + 1);
+        q.table_size = (uint32_t)next_pow2(F * h + F * h / 3 + 1);
       }
     }
     q.sw_words = (uint32_t)((T + k + 63) / 32 + 4);
@@ -1863,7 +1876,7 @@ sel_prepare(grb_ctx* c, uint64_t max_len)
   const uint64_t tiles = std::max<uint64_t>(1, max_len / T);
   if (tiles > c->sc_tiles) {
     const uint64_t cap = c->prm.cand_cap;
-    GRB_CUDA(c, c->b_stash.reserve(tiles * T * h, 0, s));
+    GRB_CUDA(c, c->b_stash.reserve(tiles * F * h, 0, s));
     GRB_CUDA(c, c->b_best_id.reserve(tiles, 0, s));
     GRB_CUDA(c, c->b_best_count.reserve(tiles, 0, s));
     GRB_CUDA(c, c->b_n_cand.reserve(tiles, 0, s));
@@ -1875,7 +1888,7 @@ sel_prepare(grb_ctx* c, uint64_t max_len)
     c->sc_tiles = tiles;
   }
   const uint64_t round_tiles = std::min<uint64_t>(tiles, 64 * c->p.block_size);
-  const uint64_t tab = next_pow2(2 * round_tiles * T * h);
+  const uint64_t tab = next_pow2(2 * round_tiles * F * h);
   if (tab > c->sc_tab) {
     c->b_tab_key.release();
     c->b_tab_mask.release();
@@ -1908,8 +1921,8 @@ launch_read(grb_ctx* c, uint64_t r, uint64_t dec_idx, grb_decision* d_dec)
   const uint64_t blocks = (tiles + c->p.block_size - 1) / c->p.block_size;
   const uint64_t rounds = std::max<uint64_t>(1, (blocks + 63) / 64);
   const uint64_t round_tiles = std::min<uint64_t>(std::max<uint64_t>(tiles, 1), 64 * c->p.block_size);
-  const uint32_t tab = (uint32_t)next_pow2(2 * round_tiles * T * h);
-  const unsigned cgrid = grid_for(round_tiles * T * h, 256, c->sm_count * 4);
+  const uint32_t tab = (uint32_t)next_pow2(2 * round_tiles * c->tile_frames * h);
+  const unsigned cgrid = grid_for(round_tiles * c->tile_frames * h, 256, c->sm_count * 4);
   const unsigned agrid = grid_for(tab, 256, c->sm_count * 4);
   for (uint64_t round = 0; round < rounds; ++round) {
     c->kbegin();
@@ -1943,7 +1956,7 @@ batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
                uint32_t max_batch_reads)
 {
   cudaStream_t s = c->stream;
-  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  const uint64_t T = c->tile_frames, h = c->h_seed.h; // T: frames per tile (stride of the per-probe buffers)
   if (max_read_tiles > 2048) {
     return c->fail(GRB_ERR_ARG, "a read spans more than 2048 tiles: raise the tile length");
   }
@@ -2019,7 +2032,7 @@ batch3_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
                uint32_t max_batch_reads)
 {
   cudaStream_t s = c->stream;
-  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  const uint64_t T = c->tile_frames, h = c->h_seed.h; // T: frames per tile
   int rc = batch2_prepare(c, max_batch_tiles, max_read_tiles, max_cm_words, max_batch_reads);
   if (rc != GRB_OK) {
     return rc;
@@ -2077,7 +2090,7 @@ static int
 launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
 {
   cudaStream_t s = c->stream;
-  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  const uint64_t T = c->tile_frames, h = c->h_seed.h; // T: frames per tile
   GrbBatchDev bd{};
   bd.read_idx = c->bb_read_idx.p + b.read0;
   bd.tile_first = c->bb_tile_first.p + b.tf0;
@@ -2308,7 +2321,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
       uint32_t max_nb = 0;
       // the commit indexes a batch's probes with 26 bits
       const uint64_t tile_budget = std::max<uint64_t>(
-        1, std::min<uint64_t>(c->batch_tiles, ((1ull << 26) - 1) / (T * c->h_seed.h)));
+        1, std::min<uint64_t>(c->batch_tiles, ((1ull << 26) - 1) / (c->tile_frames * c->h_seed.h)));
       for (; j < end && launched < kChunk; ++j) {
         if (!(c->h_flags[j] & GRB_READ_PASS2)) {
           continue;
@@ -2564,7 +2577,7 @@ grb_insert_tiles(grb_ctx* c, uint64_t read_idx, uint32_t tile_start, uint32_t ti
   GRB_CUDA(c, cudaMemcpyAsync(c->sc.plan, &plan, sizeof plan, cudaMemcpyHostToDevice, s));
   GrbSelParams q = c->prm;
   q.block_size = tiles + 1; // the whole range is ONE insert call
-  const uint64_t n = (uint64_t)(tile_end - tile_start) * T * h;
+  const uint64_t n = (uint64_t)(tile_end - tile_start) * c->tile_frames * h;
   const uint64_t tab = next_pow2(2 * n);
   DevBuf<uint64_t> key, mask;
   GRB_CUDA(c, key.reserve(tab, 0, s));

@@ -69,9 +69,9 @@ struct GrbB3
   uint32_t* m_key;  // [members] read << 16 | tile, sorted within a shared rank
   uint32_t* m_ci;   // [members] conflict index
   uint32_t* m_seen; // [members] raw id the member's read sees under the assumed plans
-  uint32_t* fbits;  // [n_bt * T bits] frame already listed
+  uint32_t* fbits;  // [n_bt * tile_frames bits] frame already listed
   uint32_t* fl_n;   // [nb] conflict frames of read b
-  uint32_t* fl;     // frame list, read b's region starts at tile_first[b] * T: tile << 20 | frame
+  uint32_t* fl;     // frame list, read b's region starts at tile_first[b] * tile_frames: tile << 20 | frame
   uint32_t* fr;     // frame records, (2 + 2h) words: tf, shared mask, old id[h], member pos[h]
   GrbReadPlan* np;  // [nb] new plan (ids relative), its id advance, assigned tiles, hit delta
   uint32_t* np_adv;
@@ -175,11 +175,11 @@ k3_mark(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
     return;
   }
   const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
-  const uint32_t per_tile = T * h;
+  const uint32_t per_tile = prm.tile_frames * h;
   for (uint32_t bt = blockIdx.x; bt < bd.n_bt; bt += gridDim.x) {
     const uint32_t b = bd.tile_read[bt];
     const uint32_t t = bt - bd.tile_first[b];
-    const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, k);
+    const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, prm.kmer);
     if (threadIdx.x == 0) {
       s_n = 0;
     }
@@ -259,13 +259,13 @@ k3_members(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
   }
   const uint32_t mask = grb3_set_mask(n_cand, (uint32_t)b3.ix_mask);
   const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
-  const uint32_t per_tile = T * h;
+  const uint32_t per_tile = prm.tile_frames * h;
   uint32_t* st_probe = k3_stage;
   uint32_t* st_slot = k3_stage + per_tile;
   for (uint32_t bt = blockIdx.x; bt < bd.n_bt; bt += gridDim.x) {
     const uint32_t b = bd.tile_read[bt];
     const uint32_t t = bt - bd.tile_first[b];
-    const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, k);
+    const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, prm.kmer);
     if (threadIdx.x == 0) {
       s_n = 0;
     }
@@ -351,7 +351,7 @@ k3_conf(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
   if (state->halt) {
     return;
   }
-  const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
+  const uint32_t T = prm.tile_frames, k = prm.k, h = prm.h; // T: per-tile frame stride
   const uint32_t n_listed = b3.counters[GRB_CTR_LISTED];
   for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_listed; li += gridDim.x * blockDim.x) {
     const uint32_t slot = b3.t_slot[li];
@@ -399,7 +399,7 @@ k3_scatter(GrbSelParams prm, GrbBatchDev bd, GrbB3 b3, const GrbSelState* __rest
   if (state->halt) {
     return;
   }
-  const uint32_t per_tile = prm.tile_len * prm.h;
+  const uint32_t per_tile = prm.tile_frames * prm.h;
   const uint32_t n_conf = b3.counters[0];
   for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n_conf; ci += gridDim.x * blockDim.x) {
     const uint32_t sidx = b3.c_sidx[ci];
@@ -483,7 +483,7 @@ k3_frames(GrbFilterDev filt, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3,
   if (state->halt) {
     return;
   }
-  const uint32_t T = prm.tile_len, h = prm.h;
+  const uint32_t T = prm.tile_frames, h = prm.h; // T: per-tile frame stride
   const uint32_t stride = 2 + 2 * h;
   // a read's frame list is shared by GRB_FRAME_SPLIT CTAs: one CTA per read left the GPU at 18 %
   // of its warps on records that are random slot reads (ncu)
@@ -689,7 +689,7 @@ grb3_read(const GrbReadsDev& reads, const GrbSelParams& prm, const GrbBatchDev& 
   const uint32_t bt0 = bd.tile_first[b];
   const uint32_t nfr = b3.fl_n[b];
   const uint32_t nu = bd.nu[b];
-  const uint32_t* fr = b3.fr + (uint64_t)bt0 * T * stride;
+  const uint32_t* fr = b3.fr + (uint64_t)bt0 * prm.tile_frames * stride;
   uint32_t* cmat = cm_smem ? sm.cmat : b3.cmat_g + (uint64_t)blockIdx.x * n_cap * n_cap;
 
   __syncthreads();
@@ -1230,7 +1230,7 @@ k3_bulk(GrbReadsDev reads, GrbFilterDev filt, GrbSelParams prm, GrbBatchDev bd, 
   }
   const uint32_t T = prm.tile_len, k = prm.k, h = prm.h;
   const uint32_t B = (uint32_t)prm.block_size;
-  const uint32_t per_tile = T * h;
+  const uint32_t per_tile = prm.tile_frames * h;
   for (uint32_t bt = blockIdx.x; bt < bd.n_bt; bt += gridDim.x) {
     const uint32_t b = bd.tile_read[bt];
     const GrbReadPlan plan = b3.plan_out[b];
@@ -1242,7 +1242,7 @@ k3_bulk(GrbReadsDev reads, GrbFilterDev filt, GrbSelParams prm, GrbBatchDev bd, 
       continue;
     }
     const uint32_t id = plan.first_id + (t - plan.trim_start) / B + plan.id_bump;
-    const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, k);
+    const uint32_t tl = grb_tile_bases(reads.len[bd.read_idx[b]], t, T, prm.kmer);
     const uint64_t* stash = bd.stash + (uint64_t)bt * per_tile;
     for (uint32_t rem = threadIdx.x; rem < per_tile; rem += blockDim.x) {
       const uint32_t f = rem / h, p = rem - f * h;

@@ -50,7 +50,7 @@ k2_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g,
     const uint32_t len = reads.len[read_idx];
     const uint64_t w_read = reads.word_off[read_idx];
     const uint32_t w_total = (len + 31) / 32;
-    const uint32_t tl = grb_tile_bases(len, t, T, k);
+    const uint32_t tl = grb_tile_bases(len, t, T, prm.kmer);
     const uint32_t frames = tl - k + 1;
     const uint32_t p0 = t * T;
     const uint32_t w_first = p0 >> 5;
@@ -69,7 +69,7 @@ k2_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g,
     }
     __syncthreads();
     uint32_t my_hits = 0, my_miss = 0;
-    uint64_t* stash = bd.stash + (uint64_t)bt * T * h;
+    uint64_t* stash = bd.stash + (uint64_t)bt * prm.tile_frames * h;
     for (uint32_t f = threadIdx.x; f < frames; f += BS) {
       uint64_t rank[GRB_MAX_PATTERNS];
       bool all = true;
@@ -289,7 +289,7 @@ k2_cmat(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB2 b2,
       for (uint32_t i = threadIdx.x; i < n; i += BS) {
         my_h += bd.tile_hits[bt0 + i];
         my_m += bd.tile_miss[bt0 + i];
-        my_q += grb_tile_bases(len, i, prm.tile_len, prm.k) - prm.k + 1;
+        my_q += grb_tile_bases(len, i, prm.tile_len, prm.kmer) - prm.k + 1;
       }
       if (my_q) {
         atomicAdd(&bd.rd_hits[b], my_h);

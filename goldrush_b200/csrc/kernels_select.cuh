@@ -17,10 +17,12 @@
 
 struct GrbSelParams
 {
-  uint32_t tile_len, k, h, cand_cap;
+  uint32_t tile_len, k, h, cand_cap; // k = span of seed pattern 0 (k - 1 for an odd -k, spaced_seeds.cpp:28,58)
   uint32_t table_size; // shared-memory vote table entries (power of two)
   uint32_t sw_words;   // shared-memory words holding one tile's bases
   int32_t silver;
+  uint32_t kmer;        // -k: a tile is cut as substr(i * T, T + kmer - 1) (read_hashing.cpp:43-46)
+  uint32_t tile_frames; // frames of a full tile = per-tile stride of the stash: T + kmer - k
   uint32_t pad;
   uint64_t threshold, unassigned_min, assigned_max, block_size, max_paths, target_bases;
 };
@@ -111,7 +113,7 @@ k_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilterD
   uint64_t my_queries = 0;
 
   for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const uint32_t tl = grb_tile_bases(len, t, T, k);
+    const uint32_t tl = grb_tile_bases(len, t, T, prm.kmer);
     const uint32_t frames = tl - k + 1;
     const uint32_t p0 = t * T;
     const uint32_t w_first = p0 >> 5;
@@ -145,7 +147,7 @@ k_query(GrbReadsDev reads, const GrbSeedTables* __restrict__ seeds_g, GrbFilterD
           bool bit;
           grb_probe_block(filt, grb_fastmod(hv, filt.bits, filt.inv), bit, rank[i]);
           all &= bit;
-          sc.stash[((uint64_t)t * T + f) * h + i] = rank[i];
+          sc.stash[((uint64_t)t * prm.tile_frames + f) * h + i] = rank[i];
         }
       }
       if (!all) { // MIBloomFilter::atRank fails on the first clear bit: the frame counts nothing
@@ -340,7 +342,7 @@ k_insert_collect(GrbReadsDev reads, GrbSelParams prm, GrbSelScratch sc,
   if (last_tile > plan.trim_end) {
     last_tile = plan.trim_end;
   }
-  const uint64_t per_tile = (uint64_t)T * h;
+  const uint64_t per_tile = (uint64_t)prm.tile_frames * h;
   const uint64_t total = (last_tile - first_tile + 1) * per_tile;
   const uint64_t mask = tab_size - 1;
   for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -349,11 +351,11 @@ k_insert_collect(GrbReadsDev reads, GrbSelParams prm, GrbSelScratch sc,
     const uint32_t rem = (uint32_t)(idx - trel * per_tile);
     const uint32_t f = rem / h, p = rem - f * h;
     const uint32_t t = (uint32_t)(first_tile + trel);
-    const uint32_t tl = grb_tile_bases(len, t, T, k);
+    const uint32_t tl = grb_tile_bases(len, t, T, prm.kmer);
     if (tl < k + p || f >= tl - (k + p) + 1) {
       continue; // stale-tail repeat of the last valid position: same rank, already registered
     }
-    const uint64_t key = stash[((uint64_t)t * T + f) * h + p] & ~(1ull << 63);
+    const uint64_t key = stash[((uint64_t)t * prm.tile_frames + f) * h + p] & ~(1ull << 63);
     const uint32_t j = (uint32_t)((t - plan.trim_start) / B) - 64u * round;
     uint64_t slot = grb_mix64(key) & mask;
     while (true) {

@@ -1003,6 +1003,13 @@ run_path(Opt& opt)
   std::cerr << "finished inserting bit vector\nin " << omp_get_wtime() - t0 << "\n";
 
   f.setup(); // :1203-1205
+  // MIBloomFilter.hpp:180: the filter's constructor asserts that seed pattern 0 spans -k; an odd -k
+  // gives a span of k - 1 (spaced_seeds.cpp:28,58-60) and the reference build (meson default:
+  // asserts on) aborts here, after pass 1
+  if (seed_strings[0].size() != opt.kmer_size) {
+    std::cerr << "Assertion `m_sseeds[0].size() == kmerSize' failed." << std::endl;
+    abort();
+  }
 
   // ---- pass 2, goldrush_path.cpp:1207-1256 + process_read :892-1094 ----
   std::cerr << "assigning tiles" << std::endl;

@@ -92,6 +92,16 @@ CASES = [
                "-M", "2", "-m", "5000", "--silver_path", "--verbose", "--ntcard"]),
 ]
 
+# odd -k: make_seed_pattern builds seeds of span k - 1 (two halves of k / 2 positions,
+# spaced_seeds.cpp:28,58-60) and the reference aborts on MIBloomFilter.hpp:180
+# (assert(m_sseeds[0].size() == kmerSize); meson's default build keeps asserts) once pass 1 is
+# done: exit by SIGABRT, no record written.  Not a fixture: checked by test_oracle_vs_ref.py
+# (reference and oracle abort alike) and test_host_logic.py (the engine refuses the option).
+ODD_K_CASE = dict(name="odd_k_aborts", synth=synth_args(60000, 10, 4000, 19),
+                  args=["-k", "23", "-w", "16", "-s", SEED22 + "0", "-h", "3", "-t", "250", "-u", "5",
+                        "-a", "1", "-o", "0.1", "-x", "10", "-b", "5", "-d", "5", "-P", "0", "-g",
+                        "6e4", "-r", "0.9", "-M", "3", "-m", "4000", "--silver_path", "--verbose"])
+
 POST = {"mutate_n_and_case": mutate_n_and_case, "ragged_tail": ragged_tail}
 
 

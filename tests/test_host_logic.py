@@ -159,6 +159,36 @@ def test_engine_fails_loudly_without_a_gpu():
                      seed_preset="1011011110110111101101")
 
 
+def test_odd_kmer_size_is_refused_before_any_device_work():
+    """An odd -k yields seeds of span k - 1 (spaced_seeds.cpp:28,58-60); the reference aborts on
+    MIBloomFilter.hpp:180 after pass 1 (tests/test_oracle_vs_ref.py), the engine says no at once."""
+    seeds = grb.make_seed_pattern("10110111101101111011010", 23, 16, 3)
+    assert [len(s) for s in seeds] == [22, 23, 24]
+    with pytest.raises(grb.GrbError) as e:
+        grb.Engine(seeds, genome_size=1000000, weight=16, kmer_size=23)
+    assert e.value.code == -1 and "MIBloomFilter.hpp:180" in str(e.value)
+
+
+def test_no_product_source_touches_the_oracle():
+    """Nothing under goldrush_b200/ or include/ may include, link or execute oracle/ (DESIGN.md 1)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bad = []
+    for base in ("goldrush_b200", "include"):
+        for d, _, files in os.walk(os.path.join(root, base)):
+            for fn in files:
+                if fn.endswith((".so", ".pyc")):
+                    continue
+                with open(os.path.join(d, fn), errors="replace") as f:
+                    txt = f.read()
+                if re.search(r'#include\s+"[^"]*oracle|libgrb_oracle|oracle/_(build|ref)|grbo_|'
+                             r"goldrush-path-(ref|oracle)|import\s+oracle", txt):
+                    bad.append(os.path.join(d, fn))
+    assert not bad, bad
+    with open(os.path.join(root, "Makefile")) as f:
+        lib_rule = f.read().split("$(LIB):")[1].split("\n\n")[0]
+    assert "oracle" not in lib_rule
+
+
 def test_synth_generator_is_deterministic_and_thread_independent():
     sp = grb.api.synth_params(50000, 3.0, 2000, 77)
     a = grb.synth_fastq(sp)

@@ -36,3 +36,18 @@ def test_oracle_equals_reference_binary(case, workdir):
     assert outs_r, "reference wrote nothing: " + err_r[-400:]
     assert pu.digest_outputs(outs_r) == pu.digest_outputs(outs_o)
     assert pu.parse_stats(err_r) == pu.parse_stats(err_o)
+
+
+def test_odd_k_aborts_in_reference_and_oracle(workdir):
+    """An odd -k gives seeds of span k - 1 and the reference dies on the assertion in the filter's
+    constructor (MIBloomFilter.hpp:180) after pass 1; the oracle mirrors that, the engine refuses
+    the option up front (test_host_logic.py)."""
+    import signal
+    case = pu.golden_cases.ODD_K_CASE
+    inp, extra = pu.make_input(case, workdir)
+    rc_r, outs_r, err_r = pu.run_cli(pu.REF, case, inp, extra, workdir, "ref", jobs=2)
+    rc_o, outs_o, err_o = pu.run_cli(pu.ORACLE, case, inp, extra, workdir, "ora", jobs=2)
+    assert rc_r == -signal.SIGABRT and rc_o == -signal.SIGABRT, (rc_r, rc_o)
+    assert "m_sseeds[0].size() == kmerSize" in err_r and "m_sseeds[0].size() == kmerSize" in err_o
+    for o in outs_r + outs_o:  # the first output file is opened before the abort and stays empty
+        assert os.path.getsize(o) == 0
