@@ -129,11 +129,11 @@ log_path_stat(const Log& log, uint64_t curr_path, const grb_path_stats& s, doubl
 
 } // namespace
 
-// `capture` (may be NULL) receives the bytes of every output record, in output order: what `cat
-// <p>_1.fq ... <p>_M.fq` would give (bin/goldrush:249-251), for grb_run_two_stage.
+// `capture` (may be NULL) receives the bytes of every output record, one buffer per output file
+// (capture[n - 1] = what <p>_n.fq holds), for grb_run_two_stage.
 static int
 run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_run_result* res,
-              char* err, size_t err_cap, std::vector<char>* capture)
+              char* err, size_t err_cap, std::vector<std::vector<char>>* capture)
 {
   const double t_wall0 = now_ms();
   const bool timing = getenv("GRB_TIMING") != nullptr; // host-side phase clock on stderr
@@ -726,12 +726,16 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
         if (out.f) {
           fwrite(buf.data() + r.at, 1, r.bytes, out.f);
         }
-        if (capture) {
-          capture->insert(capture->end(), buf.data() + r.at, buf.data() + r.at + r.bytes);
-        }
         digest.add((const char*)&r.hash, 8);
         phred_sum += r.phred;
         path_now = dec[r.read].path;
+        if (capture) {
+          if (capture->size() < path_now) {
+            capture->resize(path_now);
+          }
+          std::vector<char>& cp = (*capture)[path_now - 1];
+          cp.insert(cp.end(), buf.data() + r.at, buf.data() + r.at + r.bytes);
+        }
         if (r.closes_path) {
           if (o->verbose) {
             log_path_stat(log, path_now, snaps[snap_i], phred_sum);
@@ -834,10 +838,25 @@ grb_run_two_stage(const grb_run_options* silver, const grb_run_options* golden, 
     return set_err(err, err_cap, "grb_run_two_stage: first stage must be --silver_path, second not",
                    GRB_ERR_ARG);
   }
-  std::vector<char> paths;
-  int rc = run_path_impl(silver, fastq, fastq_len, res_silver, err, err_cap, &paths);
+  std::vector<std::vector<char>> per_path;
+  int rc = run_path_impl(silver, fastq, fastq_len, res_silver, err, err_cap, &per_path);
   if (rc != GRB_OK) {
     return rc;
+  }
+  // bin/goldrush:250-251 builds the golden run's input with `cat $(p1)_*.fq`: the shell expands the
+  // glob in lexicographic order of the file names (_1, _10, _11, _2, ...), and the selection depends
+  // on read order, so the paths are joined in that order, not numerically
+  std::vector<size_t> order(per_path.size());
+  for (size_t i = 0; i < order.size(); ++i) {
+    order[i] = i;
+  }
+  std::sort(order.begin(), order.end(), [](size_t a, size_t b) {
+    return std::to_string(a + 1) + ".fq" < std::to_string(b + 1) + ".fq";
+  });
+  std::vector<char> paths;
+  for (size_t i : order) {
+    paths.insert(paths.end(), per_path[i].begin(), per_path[i].end());
+    std::vector<char>().swap(per_path[i]);
   }
   if (paths.empty()) { // the golden run would stop on an empty file (goldrush_path.cpp:247-250)
     return set_err(err, err_cap, "grb_run_two_stage: the silver stage selected no read", GRB_ERR_FORMAT);

@@ -86,6 +86,16 @@ CASES = [
          args=["-k", "22", "-w", "16", "-s", SEED22, "-h", "3", "-t", "100", "-u", "5", "-a", "1",
                "-o", "0.15", "-x", "4", "-b", "1", "-d", "5", "-P", "13", "-g", "6e4", "-H",
                "400000", "-r", "0.9", "-M", "5", "-m", "2500", "--silver_path", "--verbose"]),
+    # more than 9 silver paths: `cat $(p1)_*.fq` (bin/goldrush:250-251) joins them in the shell's
+    # lexicographic order (_1, _10, _11, _12, _2, ...), which is the golden run's read order
+    dict(name="silver_m12", synth=synth_args(60000, 40, 3000, 21, err=0.004),
+         args=["-k", "22", "-w", "16", "-s", SEED22, "-h", "3", "-t", "250", "-u", "4", "-a", "1",
+               "-o", "0.1", "-x", "8", "-b", "3", "-d", "5", "-P", "0", "-g", "6e4", "-r", "0.5",
+               "-M", "12", "-m", "3000", "--silver_path", "--verbose"]),
+    dict(name="golden_m12", from_case="silver_m12",
+         args=["-k", "22", "-w", "16", "-s", SEED22, "-h", "3", "-t", "250", "-u", "4", "-a", "1",
+               "-o", "0.1", "-x", "8", "-b", "3", "-d", "5", "-P", "0", "-g", "6e4", "-m", "0",
+               "--verbose"]),
     dict(name="ntcard_sizing", synth=synth_args(100000, 25, 5000, 15), post="mutate_n_and_case",
          args=["-k", "22", "-w", "16", "-s", SEED22, "-h", "3", "-t", "250", "-u", "5", "-a", "1",
                "-o", "0.1", "-x", "10", "-b", "5", "-d", "5", "-P", "0", "-g", "1e5", "-r", "0.9",

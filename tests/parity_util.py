@@ -39,6 +39,8 @@ def make_input(case, workdir, produce_outputs=None):
     if "from_case" in case:
         src = case_by_name(case["from_case"])
         outs = produce_outputs(src, workdir)
+        # `cat $(p1)_*.fq` (bin/goldrush:250-251): shell glob order = lexicographic (C collation)
+        outs = sorted(outs, key=lambda o: os.path.basename(o).encode())
         with open(path, "wb") as f:
             for o in outs:
                 with open(o, "rb") as g:

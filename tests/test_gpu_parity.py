@@ -338,11 +338,13 @@ def test_cli_binary_matches_reference_fixture(name, workdir):
     assert pu.parse_stats(err) == g["stats"]
 
 
-def test_two_stage_call_equals_two_reference_runs(workdir):
-    """grb_run_two_stage (bin/goldrush:240-260 in one call): the silver files of `silver_default`
-    AND the golden path the reference wrote from their concatenation (`golden_default`), without
-    the files travelling through a second process."""
-    silver, golden = pu.case_by_name("silver_default"), pu.case_by_name("golden_default")
+@pytest.mark.parametrize("pair", [("silver_default", "golden_default"), ("silver_m12", "golden_m12")])
+def test_two_stage_call_equals_two_reference_runs(pair, workdir):
+    """grb_run_two_stage (bin/goldrush:240-260 in one call): the silver files of the silver case
+    AND the golden path the reference wrote from their concatenation, without the files travelling
+    through a second process.  With 12 paths the concatenation order is the shell glob's
+    (_1, _10, _11, _12, _2, ...), not the numeric one."""
+    silver, golden = pu.case_by_name(pair[0]), pu.case_by_name(pair[1])
     inp, extra = pu.make_input(silver, workdir, _product_outputs_for)
     with open(inp, "rb") as f:
         data = f.read()
@@ -355,8 +357,8 @@ def test_two_stage_call_equals_two_reference_runs(workdir):
     s_outs = sorted((os.path.join(workdir, fn) for fn in os.listdir(workdir)
                      if fn.startswith("two.silver")), key=lambda p: (len(p), p))
     g_outs = [os.path.join(workdir, "two.golden.fa")]
-    assert pu.digest_outputs(s_outs) == GOLDEN["silver_default"]["outputs"]
-    assert pu.digest_outputs(g_outs) == GOLDEN["golden_default"]["outputs"]
+    assert pu.digest_outputs(s_outs) == GOLDEN[pair[0]]["outputs"]
+    assert pu.digest_outputs(g_outs) == GOLDEN[pair[1]]["outputs"]
     assert rs.reads_selected > 0 and rg.reads_selected > 0
     assert rg.num_reads == rs.reads_selected  # the second stage read exactly the silver records
 
