@@ -35,6 +35,7 @@ class ReadMeta(C.Structure):
         ("hdr_off", C.c_uint64), ("seq_off", C.c_uint64), ("qual_off", C.c_uint64),
         ("hdr_len", C.c_uint32), ("len", C.c_uint32), ("phred_first_half_sum", C.c_double),
         ("phred_total_sum", C.c_double), ("non_acgt", C.c_uint32), ("qual_len", C.c_uint32),
+        ("name_hash", C.c_uint64),
     ]
 
 
@@ -67,7 +68,8 @@ class RunOptions(C.Structure):
         ("params", Params), ("seed_preset", C.c_char_p), ("prefix", C.c_char_p),
         ("filter_file", C.c_char_p), ("input_path", C.c_char_p), ("ntcard", C.c_int32),
         ("verbose", C.c_int32), ("debug", C.c_int32), ("write_outputs", C.c_int32),
-        ("quiet", C.c_int32), ("jobs", C.c_int32),
+        ("quiet", C.c_int32), ("jobs", C.c_int32), ("fastq_offset", C.c_uint64),
+        ("fastq_total", C.c_uint64),
     ]
 
 
@@ -96,7 +98,8 @@ class SynthParams(C.Structure):
 
 READ_META_DTYPE = np.dtype([("hdr_off", "<u8"), ("seq_off", "<u8"), ("qual_off", "<u8"),
                             ("hdr_len", "<u4"), ("len", "<u4"), ("phred_first_half_sum", "<f8"),
-                            ("phred_total_sum", "<f8"), ("non_acgt", "<u4"), ("qual_len", "<u4")])
+                            ("phred_total_sum", "<f8"), ("non_acgt", "<u4"), ("qual_len", "<u4"),
+                            ("name_hash", "<u8")])
 DECISION_DTYPE = np.dtype([("verdict", "u1"), ("pad", "u1", (3,)), ("path", "<u4"),
                            ("trim_start", "<u4"), ("trim_end", "<u4"), ("num_tiles", "<u4"),
                            ("num_assigned", "<u4")])
@@ -135,6 +138,10 @@ def lib():
         "grb_reads_ingest_fastq": (i32, [vp, vp, sz, i32, P(sz)]),
         "grb_reads_readahead": (i32, [vp, vp, sz]),
         "grb_reads_count": (u64, [vp]),
+        "grb_reads_set_origin": (i32, [vp, u64]),
+        "grb_reads_allgather": (i32, [vp]),
+        "grb_reads_own_range": (i32, [vp, P(u64), P(u64)]),
+        "grb_comm_allgather_host": (i32, [vp, vp, u64, vp, u64, P(u64)]),
         "grb_reads_get_meta": (i32, [vp, u64, u64, P(ReadMeta)]),
         "grb_reads_set_flags": (i32, [vp, u64, u64, vp]),
         "grb_reads_clear": (None, [vp]),
@@ -322,6 +329,18 @@ class Engine:
     def reads_count(self):
         return self._L.grb_reads_count(self._h)
 
+    def reads_set_origin(self, byte_offset):
+        self._chk(self._L.grb_reads_set_origin(self._h, int(byte_offset)))
+
+    def reads_allgather(self):
+        """Several GPUs: every rank ingested its own slice; afterwards every store holds all reads."""
+        self._chk(self._L.grb_reads_allgather(self._h))
+
+    def reads_own_range(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._chk(self._L.grb_reads_own_range(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def reads_get_meta(self, first=0, count=None):
         if count is None:
             count = self.reads_count() - first
@@ -506,6 +525,9 @@ class Engine:
 def _run_options(input_path, prefix, seed_preset, filter_file, ntcard, verbose, write_outputs,
                  quiet, device, params):
     o = RunOptions()
+    params = dict(params)
+    o.fastq_offset = int(params.pop("fastq_offset", 0))  # slice mode (several GPUs), see the header
+    o.fastq_total = int(params.pop("fastq_total", 0))
     o.params = default_params(**params)
     o.params.device = device
     o.seed_preset = (seed_preset or "").encode()

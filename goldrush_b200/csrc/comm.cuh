@@ -28,6 +28,8 @@ struct GrbNccl
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t,
+                            cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -49,7 +51,7 @@ grb_comm()
   return *g;
 }
 
-// binds the seven NCCL entry points; returns false and sets g.err if no libnccl can be found
+// binds the eight NCCL entry points; returns false and sets g.err if no libnccl can be found
 inline bool
 grb_nccl_load(GrbComm& g)
 {
@@ -73,10 +75,12 @@ grb_nccl_load(GrbComm& g)
   a.CommInitRank = (decltype(a.CommInitRank))dlsym(lib, "ncclCommInitRank");
   a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
   a.AllGather = (decltype(a.AllGather))dlsym(lib, "ncclAllGather");
+  a.Broadcast = (decltype(a.Broadcast))dlsym(lib, "ncclBroadcast");
   a.GroupStart = (decltype(a.GroupStart))dlsym(lib, "ncclGroupStart");
   a.GroupEnd = (decltype(a.GroupEnd))dlsym(lib, "ncclGroupEnd");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
-  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GroupStart ||
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.Broadcast ||
+      !a.GroupStart ||
       !a.GroupEnd || !a.GetErrorString) {
     g.err = "libnccl lacks one of the entry points this library binds";
     dlclose(lib);

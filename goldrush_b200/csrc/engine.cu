@@ -192,6 +192,9 @@ struct grb_ctx
   uint64_t n_reads = 0;
   uint64_t n_words = 0;       // packed words in use
   uint64_t ingested_bytes = 0; // running offset of the concatenated input
+  uint64_t origin_bytes = 0;   // offset of this rank's first byte within the whole input
+  uint64_t own_first = 0, own_count = 0; // after grb_reads_allgather: the reads this rank ingested
+  bool gathered = false;
   std::vector<uint32_t> h_len;
   std::vector<uint64_t> h_word_off;
   std::vector<uint8_t> h_flags;
@@ -850,6 +853,9 @@ grb_reads_clear(grb_ctx* c)
   c->n_reads = 0;
   c->n_words = 0;
   c->ingested_bytes = 0;
+  c->origin_bytes = 0;
+  c->own_first = c->own_count = 0;
+  c->gathered = false;
   c->h_len.clear();
   c->h_word_off.clear();
   c->h_flags.clear();
@@ -905,7 +911,10 @@ grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_
   if (n > (1ull << 31)) {
     return c->fail(GRB_ERR_ARG, "grb_reads_ingest_fastq: chunk larger than 2 GiB");
   }
-  if (c->ingested_bytes == 0 && c->n_reads == 0 && bytes[0] != '@') {
+  if (c->gathered) {
+    return c->fail(GRB_ERR_STATE, "grb_reads_ingest_fastq after grb_reads_allgather");
+  }
+  if (c->ingested_bytes == c->origin_bytes && c->n_reads == 0 && bytes[0] != '@') {
     return c->fail(GRB_ERR_FORMAT, "Gold Path requires fastq format");
   }
   cudaStream_t s = c->stream;
@@ -1047,6 +1056,204 @@ grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_
   c->n_words += new_words;
   *consumed = (4 * n_rec - 1 < n_nl) ? (size_t)last_nl + 1 : n;
   c->ingested_bytes += *consumed;
+  return GRB_OK;
+}
+
+int
+grb_reads_set_origin(grb_ctx* c, uint64_t byte_offset)
+{
+  if (c->n_reads != 0 || c->ingested_bytes != c->origin_bytes) {
+    return c->fail(GRB_ERR_STATE, "grb_reads_set_origin after the first grb_reads_ingest_fastq");
+  }
+  c->origin_bytes = byte_offset;
+  c->ingested_bytes = byte_offset;
+  return GRB_OK;
+}
+
+int
+grb_reads_own_range(const grb_ctx* c, uint64_t* first, uint64_t* count)
+{
+  *first = c->gathered ? c->own_first : 0;
+  *count = c->gathered ? c->own_count : c->n_reads;
+  return GRB_OK;
+}
+
+// Every rank holds the reads of its own slice of the input; afterwards every rank holds all of
+// them, in rank (= file) order.  The packed stores travel device to device (one NCCL broadcast per
+// rank and array, grouped); the per-read metadata is small and goes host -> device -> all -> host.
+int
+grb_reads_allgather(grb_ctx* c)
+{
+  cudaSetDevice(c->device);
+  if (c->gathered) {
+    return c->fail(GRB_ERR_STATE, "grb_reads_allgather called twice");
+  }
+  c->gathered = true;
+  c->own_first = 0;
+  c->own_count = c->n_reads;
+  if (!c->comm) {
+    return GRB_OK;
+  }
+  GrbComm& g = *c->comm;
+  const int W = g.world, me = g.rank;
+  cudaStream_t s = c->stream;
+  if (c->copy_stream) {
+    GRB_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  }
+  c->tic();
+  // ---- how much every rank brings ----
+  DevBuf<uint64_t> d_cnt;
+  GRB_CUDA(c, d_cnt.reserve(2 * (size_t)W, 0, s));
+  const uint64_t mine[2] = { c->n_reads, c->n_words };
+  GRB_CUDA(c, cudaMemcpyAsync(d_cnt.p + 2 * me, mine, 16, cudaMemcpyHostToDevice, s));
+  ncclResult_t r = g.api.AllGather(d_cnt.p + 2 * me, d_cnt.p, 2, ncclUint64, g.comm, s);
+  if (r != ncclSuccess) {
+    return c->fail_nccl(r, "ncclAllGather (read counts)");
+  }
+  std::vector<uint64_t> cnt(2 * (size_t)W);
+  GRB_CUDA(c, cudaMemcpyAsync(cnt.data(), d_cnt.p, cnt.size() * 8, cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  std::vector<uint64_t> r0(W + 1, 0), w0(W + 1, 0);
+  for (int q = 0; q < W; ++q) {
+    r0[q + 1] = r0[q] + cnt[2 * q];
+    w0[q + 1] = w0[q] + cnt[2 * q + 1];
+  }
+  const uint64_t n_reads = r0[W], n_words = w0[W];
+  // ---- packed bases + masks, device to device ----
+  DevBuf<uint64_t> nb;
+  DevBuf<uint32_t> nm;
+  DevBuf<grb_read_meta> dm;
+  GRB_CUDA(c, nb.reserve_exact(n_words + 4, s));
+  GRB_CUDA(c, nm.reserve_exact(n_words + 4, s));
+  GRB_CUDA(c, dm.reserve_exact(std::max<uint64_t>(1, n_reads), s));
+  if (c->n_words) {
+    GRB_CUDA(c, cudaMemcpyAsync(nb.p + w0[me], c->d_bases.p, c->n_words * 8, cudaMemcpyDeviceToDevice, s));
+    GRB_CUDA(c, cudaMemcpyAsync(nm.p + w0[me], c->d_nmask.p, c->n_words * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  if (c->n_reads) {
+    GRB_CUDA(c, cudaMemcpyAsync(dm.p + r0[me], c->h_meta.data(), c->n_reads * sizeof(grb_read_meta),
+                                cudaMemcpyHostToDevice, s));
+  }
+  GRB_CUDA(c, cudaMemsetAsync(nb.p + n_words, 0, 4 * 8, s));
+  GRB_CUDA(c, cudaMemsetAsync(nm.p + n_words, 0, 4 * 4, s));
+  r = g.api.GroupStart();
+  for (int q = 0; q < W && r == ncclSuccess; ++q) {
+    if (cnt[2 * q + 1]) {
+      r = g.api.Broadcast(nb.p + w0[q], nb.p + w0[q], cnt[2 * q + 1] * 8, ncclUint8, q, g.comm, s);
+      if (r == ncclSuccess) {
+        r = g.api.Broadcast(nm.p + w0[q], nm.p + w0[q], cnt[2 * q + 1] * 4, ncclUint8, q, g.comm, s);
+      }
+    }
+    if (r == ncclSuccess && cnt[2 * q]) {
+      r = g.api.Broadcast(dm.p + r0[q], dm.p + r0[q], cnt[2 * q] * sizeof(grb_read_meta), ncclUint8, q,
+                          g.comm, s);
+    }
+  }
+  const ncclResult_t r2 = g.api.GroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess) {
+    return c->fail_nccl(r != ncclSuccess ? r : r2, "ncclBroadcast (read store)");
+  }
+  c->h_meta.resize(n_reads);
+  if (n_reads) {
+    GRB_CUDA(c, cudaMemcpyAsync(c->h_meta.data(), dm.p, n_reads * sizeof(grb_read_meta),
+                                cudaMemcpyDeviceToHost, s));
+  }
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  std::swap(c->d_bases.p, nb.p);
+  std::swap(c->d_bases.cap, nb.cap);
+  std::swap(c->d_nmask.p, nm.p);
+  std::swap(c->d_nmask.cap, nm.cap);
+  // ---- per-read arrays: every read starts on a word boundary, so the offsets follow from the lengths ----
+  c->h_len.resize(n_reads);
+  c->h_word_off.resize(n_reads);
+  c->h_flags.assign(n_reads, 0);
+  uint64_t w = 0;
+  for (uint64_t i = 0; i < n_reads; ++i) {
+    c->h_len[i] = c->h_meta[i].len;
+    c->h_word_off[i] = w;
+    c->h_flags[i] = c->h_meta[i].non_acgt ? 4 : 0;
+    w += (c->h_meta[i].len + 31) / 32;
+  }
+  if (w != n_words) {
+    return c->fail(GRB_ERR_STATE, "grb_reads_allgather: word count does not match the read lengths");
+  }
+  GRB_CUDA(c, c->d_word_off.reserve(std::max<uint64_t>(1, n_reads), 0, s));
+  GRB_CUDA(c, c->d_len.reserve(std::max<uint64_t>(1, n_reads), 0, s));
+  GRB_CUDA(c, c->d_flags.reserve(std::max<uint64_t>(1, n_reads), 0, s));
+  if (n_reads) {
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_word_off.p, c->h_word_off.data(), n_reads * 8, cudaMemcpyHostToDevice, s));
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_len.p, c->h_len.data(), n_reads * 4, cudaMemcpyHostToDevice, s));
+    GRB_CUDA(c, cudaMemcpyAsync(c->d_flags.p, c->h_flags.data(), n_reads, cudaMemcpyHostToDevice, s));
+  }
+  c->toc();
+  c->own_first = r0[me];
+  c->own_count = cnt[2 * me];
+  c->n_reads = n_reads;
+  c->n_words = n_words;
+  c->launches += 1;
+  return GRB_OK;
+}
+
+int
+grb_comm_allgather_host(grb_ctx* c, const void* send, uint64_t n, void* out, uint64_t out_cap,
+                        uint64_t* sizes)
+{
+  cudaSetDevice(c->device);
+  if (!c->comm) {
+    if (n > out_cap) {
+      return c->fail(GRB_ERR_ARG, "grb_comm_allgather_host: output buffer too small");
+    }
+    memcpy(out, send, n);
+    if (sizes) {
+      sizes[0] = n;
+    }
+    return GRB_OK;
+  }
+  GrbComm& g = *c->comm;
+  const int W = g.world, me = g.rank;
+  cudaStream_t s = c->stream;
+  DevBuf<uint64_t> d_cnt;
+  GRB_CUDA(c, d_cnt.reserve((size_t)W, 0, s));
+  GRB_CUDA(c, cudaMemcpyAsync(d_cnt.p + me, &n, 8, cudaMemcpyHostToDevice, s));
+  ncclResult_t r = g.api.AllGather(d_cnt.p + me, d_cnt.p, 1, ncclUint64, g.comm, s);
+  if (r != ncclSuccess) {
+    return c->fail_nccl(r, "ncclAllGather (sizes)");
+  }
+  std::vector<uint64_t> cnt((size_t)W);
+  GRB_CUDA(c, cudaMemcpyAsync(cnt.data(), d_cnt.p, (size_t)W * 8, cudaMemcpyDeviceToHost, s));
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  uint64_t total = 0, most = 0;
+  for (int q = 0; q < W; ++q) {
+    total += cnt[q];
+    most = std::max(most, cnt[q]);
+    if (sizes) {
+      sizes[q] = cnt[q];
+    }
+  }
+  if (total > out_cap) {
+    return c->fail(GRB_ERR_ARG, "grb_comm_allgather_host: output buffer too small");
+  }
+  if (most == 0) {
+    return GRB_OK;
+  }
+  const uint64_t pad = (most + 15) / 16 * 16;
+  DevBuf<uint8_t> stage;
+  GRB_CUDA(c, stage.reserve_exact(pad * (uint64_t)W, s));
+  if (n) {
+    GRB_CUDA(c, cudaMemcpyAsync(stage.p + pad * me, send, n, cudaMemcpyHostToDevice, s));
+  }
+  r = g.api.AllGather(stage.p + pad * me, stage.p, pad, ncclUint8, g.comm, s);
+  if (r != ncclSuccess) {
+    return c->fail_nccl(r, "ncclAllGather (host strings)");
+  }
+  uint64_t at = 0;
+  for (int q = 0; q < W; ++q) {
+    if (cnt[q]) {
+      GRB_CUDA(c, cudaMemcpyAsync((char*)out + at, stage.p + pad * q, cnt[q], cudaMemcpyDeviceToHost, s));
+    }
+    at += cnt[q];
+  }
+  GRB_CUDA(c, cudaStreamSynchronize(s));
   return GRB_OK;
 }
 
@@ -2561,7 +2768,7 @@ grb_insert_tiles(grb_ctx* c, uint64_t read_idx, uint32_t tile_start, uint32_t ti
     return rc;
   }
   cudaStream_t s = c->stream;
-  const uint64_t T = c->p.tile_length, h = c->h_seed.h;
+  const uint64_t h = c->h_seed.h;
   DevBuf<GrbSelState> tmp;
   GRB_CUDA(c, tmp.reserve(1, 0, s));
   GRB_CUDA(c, cudaMemsetAsync(tmp.p, 0, sizeof(GrbSelState), s));

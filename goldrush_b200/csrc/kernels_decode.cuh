@@ -161,6 +161,13 @@ k_records(const uint8_t* __restrict__ buf, uint64_t n_bytes, const uint32_t* __r
   m.phred_total_sum = 0.0;
   m.non_acgt = 0;
   m.qual_len = (uint32_t)(e[3] - b[3]);
+  // record id = header up to the first blank or tab (btllib Record::id): FNV-1a, the key under which
+  // the host looks a read up among the names dropped in pass 1 / listed by -f
+  uint64_t hsh = 1469598103934665603ull;
+  for (uint64_t q = b[0] + 1; q < e[0] && buf[q] != ' ' && buf[q] != '\t'; ++q) {
+    hsh = (hsh ^ buf[q]) * 1099511628211ull;
+  }
+  m.name_hash = hsh;
   meta[r] = m;
   words_per_read[r] = (m.len + 31) / 32;
 }

@@ -74,6 +74,40 @@ struct OutFile
   }
 };
 
+// first byte >= from at which a FASTQ record starts: a line that begins with '@' and whose line
+// after next begins with '+' (a quality line may begin with '@' too, but then the line after
+// next is a sequence).  n if there is none.
+size_t
+next_record_start(const char* d, size_t n, size_t from)
+{
+  if (from == 0) {
+    return 0;
+  }
+  size_t line = from;
+  if (d[from - 1] != '\n') {
+    const char* nl = (const char*)memchr(d + from, '\n', n - from);
+    if (!nl) {
+      return n;
+    }
+    line = (size_t)(nl - d) + 1;
+  }
+  while (line < n) {
+    const char* e1 = (const char*)memchr(d + line, '\n', n - line);
+    if (!e1) {
+      return n;
+    }
+    const size_t l1 = (size_t)(e1 - d) + 1;
+    if (d[line] == '@' && l1 < n) {
+      const char* e2 = (const char*)memchr(d + l1, '\n', n - l1);
+      if (e2 && (size_t)(e2 - d) + 1 < n && e2[1] == '+') {
+        return line;
+      }
+    }
+    line = l1;
+  }
+  return n;
+}
+
 double
 now_ms()
 {
@@ -221,6 +255,14 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   auto fail = [&](int code) { return set_err(err, err_cap, grb_last_error(ctx), code); };
 
   int c_world_now = 1;
+  bool shard_ingest = false;
+  const bool slice_mode = o->fastq_total != 0;
+  if (slice_mode && o->write_outputs) {
+    return set_err(err, err_cap, "slice mode (fastq_total != 0) cannot write output files: no rank "
+                                 "holds the whole input", GRB_ERR_ARG);
+  }
+  // byte `off` of the whole input, as this process can address it (slice mode: own reads only)
+  const uint64_t data_origin = slice_mode ? o->fastq_offset : 0;
   bool early = false; // pass 1 already done chunk by chunk during the ingest
   uint64_t early_bits = 0;
   double early_ms = 0;
@@ -232,21 +274,42 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     return set_err(err, err_cap, "Gold Path requires fastq format", GRB_ERR_FORMAT);
   }
   {
-    if ((rc = grb_reads_reserve(ctx, n)) != GRB_OK) {
+    int c_rank = 0, c_world = 1; // several GPUs: each rank ingests its own share of the input
+    grb_comm_info(ctx, &c_rank, &c_world);
+    c_world_now = c_world;
+    // the share of this rank: the whole buffer (one GPU, or slice mode: the caller cut the input),
+    // else bytes [cut(r), cut(r + 1)) with the cuts moved forward to record boundaries
+    size_t lo = 0, hi = n;
+    {
+      const char* e = getenv("GRB_SHARD_INGEST");
+      shard_ingest = c_world > 1 && !(e && strcmp(e, "0") == 0);
+    }
+    if (slice_mode) {
+      shard_ingest = c_world > 1;
+      if ((rc = grb_reads_set_origin(ctx, o->fastq_offset)) != GRB_OK) {
+        return fail(rc);
+      }
+    } else if (shard_ingest) {
+      lo = next_record_start(data, n, (size_t)((unsigned __int128)n * (unsigned)c_rank / (unsigned)c_world));
+      hi = c_rank + 1 == c_world
+             ? n
+             : next_record_start(data, n, (size_t)((unsigned __int128)n * (unsigned)(c_rank + 1) / (unsigned)c_world));
+      if ((rc = grb_reads_set_origin(ctx, lo)) != GRB_OK) {
+        return fail(rc);
+      }
+    }
+    if ((rc = grb_reads_reserve(ctx, hi - lo)) != GRB_OK) {
       return fail(rc);
     }
     const size_t kChunk = (size_t)1 << 30;
-    size_t off = 0;
-    if ((rc = grb_reads_readahead(ctx, data, n)) != GRB_OK) { // next chunk's copy under this one's decode
+    size_t off = lo;
+    if ((rc = grb_reads_readahead(ctx, data + lo, hi - lo)) != GRB_OK) { // next chunk's copy under this one's decode
       return fail(rc);
     }
     // Pass 1 under the ingest: when the filter size and the Phred threshold do not depend on the
     // whole file (-P given, no --ntcard), a read's pass-1 verdict (goldrush_path.cpp:261-301) only
     // needs its own record, so each chunk's reads are hashed into the bit vector while the next
     // chunk is still crossing PCIe.  The regular filter stage below re-derives the same flags.
-    int c_rank = 0, c_world = 1; // several GPUs: each rank hashes its share of every chunk
-    grb_comm_info(ctx, &c_rank, &c_world);
-    c_world_now = c_world;
     {
       const char* e = getenv("GRB_EARLY_PASS1");
       early = p.phred_min != 0 && (p.hash_universe != 0 || !o->ntcard) && !(e && strcmp(e, "0") == 0);
@@ -262,9 +325,9 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     }
     uint64_t early_done = 0;
     std::vector<grb_read_meta> cm;
-    while (off < n) {
-      const size_t len = std::min(kChunk, n - off);
-      const int final = off + len == n;
+    while (off < hi) {
+      const size_t len = std::min(kChunk, hi - off);
+      const int final = off + len == hi;
       size_t used = 0;
       const double t_c0 = now_ms();
       if ((rc = grb_reads_ingest_fastq(ctx, data + off, len, final, &used)) != GRB_OK) {
@@ -295,8 +358,10 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
                                             ? GRB_READ_PASS1
                                             : 0;
           }
-          const uint64_t my_lo = early_done + cnt * (uint64_t)c_rank / (uint64_t)c_world;
-          const uint64_t my_hi = early_done + cnt * (uint64_t)(c_rank + 1) / (uint64_t)c_world;
+          // own slice ingested: all of the chunk's reads are this rank's; whole input on every
+          // rank (GRB_SHARD_INGEST=0): an equal share of each chunk
+          const uint64_t my_lo = shard_ingest ? early_done : early_done + cnt * (uint64_t)c_rank / (uint64_t)c_world;
+          const uint64_t my_hi = shard_ingest ? now : early_done + cnt * (uint64_t)(c_rank + 1) / (uint64_t)c_world;
           if ((rc = grb_reads_set_flags(ctx, early_done, cnt, early_flags.data() + early_done)) != GRB_OK ||
               (rc = grb_build_bitvector_range(ctx, my_lo, my_hi - my_lo)) != GRB_OK) {
             log("%s\n", grb_last_error(ctx));
@@ -312,8 +377,16 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
       }
     }
     grb_reads_readahead(ctx, nullptr, 0);
+    if (shard_ingest) { // every rank's store now holds all reads, in file order (NVLink)
+      if ((rc = grb_reads_allgather(ctx)) != GRB_OK) {
+        return fail(rc);
+      }
+      R.ms_ingest += grb_last_device_ms(ctx);
+    }
   }
   mark("create+ingest");
+  uint64_t own_first = 0, own_count = 0;
+  grb_reads_own_range(ctx, &own_first, &own_count);
   const uint64_t nreads = grb_reads_count(ctx);
   std::vector<grb_read_meta> meta(nreads);
   if (nreads && (rc = grb_reads_get_meta(ctx, 0, nreads, meta.data())) != GRB_OK) {
@@ -418,8 +491,9 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   // confirmed by comparing the strings.
   std::vector<uint8_t> flags(nreads, 0);
   uint64_t by_len = 0, by_phred = 0, by_delta = 0, by_bases = 0, passed = 0;
+  auto have_bytes = [&](uint64_t i) { return !slice_mode || (i >= own_first && i < own_first + own_count); };
   auto id_span = [&](uint64_t i, const char** s0) {
-    const char* hdr = data + meta[i].hdr_off;
+    const char* hdr = data + (meta[i].hdr_off - data_origin);
     size_t l = 0;
     while (l < meta[i].hdr_len && hdr[l] != ' ' && hdr[l] != '\t') {
       ++l;
@@ -453,12 +527,9 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     R.bases_pass1 += meta[i].len;
     flags[i] = GRB_READ_PASS1;
   }
-  std::vector<uint64_t> name_hash(nreads);
-#pragma omp parallel for schedule(static) num_threads(n_threads)
-  for (int64_t i = 0; i < (int64_t)nreads; ++i) {
-    const char* s0;
-    const size_t l = id_span((uint64_t)i, &s0);
-    name_hash[i] = hash_bytes(s0, l);
+  std::vector<uint64_t> name_hash(nreads); // FNV-1a of the record id, computed by K1 (k_records)
+  for (uint64_t i = 0; i < nreads; ++i) {
+    name_hash[i] = meta[i].name_hash;
   }
   struct Dropped
   {
@@ -482,6 +553,9 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     if (it == drop_list.end() || it->hash != name_hash[i]) {
       return false;
     }
+    if (!have_bytes(i)) {
+      return true; // slice mode, another rank's read: the 64-bit hash of the id stands for the id
+    }
     const char* s0;
     const size_t l = id_span(i, &s0);
     for (; it != drop_list.end() && it->hash == name_hash[i]; ++it) {
@@ -490,6 +564,9 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
           return true;
         }
         continue;
+      }
+      if (!have_bytes((uint64_t)it->read)) {
+        return true;
       }
       const char* t0;
       const size_t tl = id_span((uint64_t)it->read, &t0);
@@ -514,9 +591,10 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   const uint64_t filter_bits = grb_calc_optimal_size(p.hash_universe, 1, p.occupancy);
   log("m_filterSize: %llu\n", (unsigned long long)filter_bits);
   if (early) { // the early pass must have used this very size and these very flags
-    early = filter_bits == early_bits && early_flags.size() == nreads;
-    for (uint64_t i = 0; early && i < nreads; ++i) {
-      early = (flags[i] & GRB_READ_PASS1) == early_flags[i];
+    const uint64_t e0 = shard_ingest ? own_first : 0;
+    early = filter_bits == early_bits && early_flags.size() == (shard_ingest ? own_count : nreads);
+    for (uint64_t i = 0; early && i < early_flags.size(); ++i) {
+      early = (flags[e0 + i] & GRB_READ_PASS1) == early_flags[i];
     }
   }
   if (!early && (rc = grb_filter_alloc(ctx, filter_bits)) != GRB_OK) {
@@ -595,6 +673,20 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     uint64_t hash;
   };
   std::vector<Rec> recs;
+  // slice mode: this rank assembles (and hashes) only the records of its own reads; the digest and
+  // the path log lines are replayed from the exchanged per-record {hash, Phred sum} pairs afterwards
+  struct Sel
+  {
+    uint64_t read;
+    bool closes_path;
+  };
+  struct HashPhred
+  {
+    uint64_t hash;
+    double phred;
+  };
+  std::vector<Sel> sel_order;
+  std::vector<HashPhred> own_pairs;
   const uint64_t T = p.tile_length;
   uint64_t visited_reads = 0;
   bool past_end = false; // a GRB_NOT_VISITED read was seen: nothing after it was reached
@@ -641,20 +733,27 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
                                                : (size_t)(d.trim_end - d.trim_start + 1) * T;
       }
       r.ql = std::min<size_t>(r.sl, meta[i].qual_len > r.s0 ? meta[i].qual_len - r.s0 : 0);
-      const char* hdr = data + meta[i].hdr_off;
+      // silver_path_check (goldrush_path.cpp:156-187): a snapshot was taken right after this read
+      r.closes_path = snap_a < snaps_seen && snaps[snap_a].rollover_read == i;
+      if (r.closes_path) {
+        ++snap_a;
+      }
+      ++R.reads_selected;
+      if (slice_mode) {
+        sel_order.push_back(Sel{ i, r.closes_path });
+        if (!have_bytes(i)) {
+          R.bases_selected += r.sl;
+          continue;
+        }
+      }
+      const char* hdr = data + (meta[i].hdr_off - data_origin);
       uint32_t l = 0;
       while (l < meta[i].hdr_len && hdr[l] != ' ' && hdr[l] != '\t') {
         ++l;
       }
       r.id_len = l;
       r.bytes = 1 + l + (r.trimmed ? 9 : 11) + r.sl + 1 + (p.silver_path ? 2 + r.ql + 1 : 0);
-      // silver_path_check (goldrush_path.cpp:156-187): a snapshot was taken right after this read
-      r.closes_path = snap_a < snaps_seen && snaps[snap_a].rollover_read == i;
-      if (r.closes_path) {
-        ++snap_a;
-      }
       recs.push_back(r);
-      ++R.reads_selected;
       R.bases_selected += r.sl;
     }
     size_t r0 = 0;
@@ -686,7 +785,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
           }
           char* w = dst;
           *w++ = first_char;
-          memcpy(w, data + m.hdr_off, r.id_len);
+          memcpy(w, data + (m.hdr_off - data_origin), r.id_len);
           w += r.id_len;
           if (r.trimmed) {
             memcpy(w, "_trimmed\n", 9);
@@ -695,14 +794,14 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
             memcpy(w, "_untrimmed\n", 11);
             w += 11;
           }
-          const char* sq = data + m.seq_off + r.s0;
+          const char* sq = data + (m.seq_off - data_origin) + r.s0;
           for (size_t j = 0; j < r.sl; ++j) { // SeqReader folds the sequence to upper case
             const unsigned char ch = (unsigned char)sq[j];
             w[j] = (char)(ch - (((unsigned)(ch - 'a') < 26u) << 5));
           }
           w += r.sl;
           *w++ = '\n';
-          const char* ql = data + m.qual_off + r.s0;
+          const char* ql = data + (m.qual_off - data_origin) + r.s0;
           if (p.silver_path) {
             *w++ = '+';
             *w++ = '\n';
@@ -723,6 +822,18 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
       }
       for (size_t ri = r0; ri < r1; ++ri) {
         const Rec& r = recs[ri];
+        if (slice_mode) {
+          own_pairs.push_back(HashPhred{ r.hash, r.phred });
+          if (capture) {
+            const uint32_t pth = dec[r.read].path;
+            if (capture->size() < pth) {
+              capture->resize(pth);
+            }
+            std::vector<char>& cp = (*capture)[pth - 1];
+            cp.insert(cp.end(), buf.data() + r.at, buf.data() + r.at + r.bytes);
+          }
+          continue;
+        }
         if (out.f) {
           fwrite(buf.data() + r.at, 1, r.bytes, out.f);
         }
@@ -786,6 +897,36 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   if (sel_rc != GRB_OK) {
     return fail(sel_rc);
   }
+  if (slice_mode) {
+    // records of rank r follow those of rank r - 1 (file order): the pairs of all ranks, back to
+    // back, line up with sel_order
+    std::vector<HashPhred> all(sel_order.size());
+    std::vector<uint64_t> sizes((size_t)std::max(1, c_world_now));
+    if ((rc = grb_comm_allgather_host(ctx, own_pairs.data(), own_pairs.size() * sizeof(HashPhred),
+                                      all.data(), all.size() * sizeof(HashPhred), sizes.data())) != GRB_OK) {
+      return fail(rc);
+    }
+    uint64_t got = 0;
+    for (uint64_t v : sizes) {
+      got += v;
+    }
+    if (got != all.size() * sizeof(HashPhred)) {
+      return set_err(err, err_cap, "slice mode: the ranks' record lists do not add up to the selection",
+                     GRB_ERR_STATE);
+    }
+    for (size_t j = 0; j < all.size(); ++j) {
+      digest.add((const char*)&all[j].hash, 8);
+      phred_sum += all[j].phred;
+      path_now = dec[sel_order[j].read].path;
+      if (sel_order[j].closes_path) {
+        if (o->verbose) {
+          log_path_stat(log, path_now, snaps[snap_i], phred_sum);
+        }
+        ++snap_i;
+        phred_sum = 0;
+      }
+    }
+  }
   grb_path_stats cur{};
   uint64_t curr_path = 1;
   if ((rc = grb_select_state(ctx, &cur, &curr_path, nullptr)) != GRB_OK) {
@@ -808,6 +949,31 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
       log_path_stat(log, curr_path, cur, phred_sum);
     }
     log("assigned\nin %.4f\n", R.ms_pass2 / 1e3);
+  }
+  if (capture && slice_mode && c_world_now > 1) {
+    // two-stage call in slice mode: every rank holds the records of its own reads only; each path
+    // is put together from the ranks' parts (rank order = read order) on every rank
+    const uint32_t n_paths = (uint32_t)std::min<uint64_t>(curr_path, std::max<uint64_t>(1, p.max_paths));
+    capture->resize(n_paths);
+    std::vector<uint64_t> sizes((size_t)c_world_now);
+    for (uint32_t q = 0; q < n_paths; ++q) {
+      std::vector<char>& part = (*capture)[q];
+      uint64_t mine = part.size(), total = 0;
+      std::vector<uint64_t> all_sizes((size_t)c_world_now);
+      if ((rc = grb_comm_allgather_host(ctx, &mine, 8, all_sizes.data(), all_sizes.size() * 8,
+                                        sizes.data())) != GRB_OK) {
+        return fail(rc);
+      }
+      for (uint64_t v : all_sizes) {
+        total += v;
+      }
+      std::vector<char> whole(total);
+      if ((rc = grb_comm_allgather_host(ctx, part.data(), part.size(), whole.data(), whole.size(),
+                                        sizes.data())) != GRB_OK) {
+        return fail(rc);
+      }
+      part.swap(whole);
+    }
   }
   R.launches = grb_launch_count(ctx);
   R.out_digest = digest.h;
@@ -862,6 +1028,7 @@ grb_run_two_stage(const grb_run_options* silver, const grb_run_options* golden, 
     return set_err(err, err_cap, "grb_run_two_stage: the silver stage selected no read", GRB_ERR_FORMAT);
   }
   grb_run_options g = *golden;
+  g.fastq_offset = g.fastq_total = 0; // the joined silver paths are whole on every rank
   if (!g.input_path) {
     g.input_path = "(silver paths in memory)";
   }

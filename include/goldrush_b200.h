@@ -104,6 +104,8 @@ typedef struct grb_read_meta
   double phred_total_sum;
   uint32_t non_acgt; /* 1 if the sequence holds a byte outside ACGTacgt (goldrush_path.cpp:293) */
   uint32_t qual_len; /* bytes of the quality line (the n of calc_phred_average) */
+  uint64_t name_hash; /* FNV-1a of the record id = header up to the first blank (btllib Record::id,
+                         the key of filter_out_reads, goldrush_path.cpp:266-299,919-932) */
 } grb_read_meta;
 
 /* Decodes every complete 4-line record in bytes[0, n) and appends it to the read store.
@@ -115,6 +117,17 @@ int grb_reads_ingest_fastq(grb_ctx* ctx, const char* bytes, size_t n, int final,
  * the next one's bytes are already copied on a second stream.  base = NULL switches it off; the
  * range must stay valid until the last chunk has been ingested. */
 int grb_reads_readahead(grb_ctx* ctx, const char* base, size_t total);
+/* Byte offset of the first ingested byte within the whole input (default 0): the offsets in
+ * grb_read_meta are relative to the whole file.  Before the first grb_reads_ingest_fastq only.
+ * Used when a rank ingests its own slice of the file (several GPUs). */
+int grb_reads_set_origin(grb_ctx* ctx, uint64_t byte_offset);
+/* Several GPUs: every rank has ingested its own consecutive slice of the input (rank order = file
+ * order); afterwards every rank's store holds ALL reads in file order -- packed bases, masks and
+ * grb_read_meta travel over NVLink (NCCL broadcasts), 0.28 bytes per base instead of 2 bytes per base
+ * and rank over PCIe.  No-op for a context without communicator.  Collective: every rank calls it. */
+int grb_reads_allgather(grb_ctx* ctx);
+/* reads [*first, *first + *count) of the store are the ones this rank ingested itself */
+int grb_reads_own_range(const grb_ctx* ctx, uint64_t* first, uint64_t* count);
 uint64_t grb_reads_count(const grb_ctx* ctx);
 int grb_reads_get_meta(grb_ctx* ctx, uint64_t first, uint64_t count, grb_read_meta* out);
 /* per-read flags decided by the host from grb_read_meta (length / Phred / delta / ACGT / -f list) */
@@ -235,6 +248,12 @@ void grb_comm_destroy(void);
 int grb_bitvector_or_reduce(grb_ctx* ctx);
 /* ctx == NULL: the process-wide communicator; else what this context uses (0 / 1 if unsharded) */
 int grb_comm_info(const grb_ctx* ctx, int* rank, int* world);
+/* Host-side all-gather of variable-length byte strings through the context's communicator (staged
+ * through device memory): rank r contributes send[0, n); out (caller-allocated, capacity out_cap)
+ * receives the strings of ranks 0..W-1 back to back, sizes[r] = bytes of rank r.  A context
+ * without communicator copies send to out.  Collective. */
+int grb_comm_allgather_host(grb_ctx* ctx, const void* send, uint64_t n, void* out, uint64_t out_cap,
+                            uint64_t* sizes);
 
 /* ---- plumbing for callers that issue their own collectives (e.g. torch.distributed) on the raw
  * device pointers ---- */
@@ -313,6 +332,13 @@ typedef struct grb_run_options
   int32_t write_outputs;   /* 0: decide only (bench) */
   int32_t quiet;           /* 1: no stderr text at all */
   int32_t jobs;            /* -j: host threads for the host-side bookkeeping (0 = default) */
+  /* Several GPUs, slice mode: `fastq` holds only bytes [fastq_offset, fastq_offset + fastq_len) of an
+   * input of fastq_total bytes, starting and ending at record boundaries, rank r's slice following
+   * rank r-1's (fastq_total = 0: `fastq` is the whole input and each rank cuts its own share out of
+   * it).  A rank then touches no byte of another rank's reads: the record digest is assembled from
+   * per-record hashes exchanged between the ranks, and write_outputs must be 0. */
+  uint64_t fastq_offset;
+  uint64_t fastq_total;
 } grb_run_options;
 
 typedef struct grb_run_result

@@ -97,6 +97,49 @@ def main():
                                  "num_passed_reads": res.num_passed_reads, "launches": res.launches}
         dist.barrier()
 
+    # ---- both launches of one assembly in one call, every rank holding the whole input ----
+    os.environ.pop("GRB_SHARD_QUERY", None)
+    silver, golden = pu.case_by_name("silver_default"), pu.case_by_name("golden_default")
+    inp, _ = pu.make_input(silver, work, outputs_for)
+    with open(inp, "rb") as f:
+        fq = f.read()
+    ps, pg = os.path.join(work, "two.silver"), os.path.join(work, "two.golden")
+    rs, rg = grb.run_two_stage(fq, dict(prefix=ps, **_args_to_params(silver["args"])),
+                               dict(prefix=pg, **_args_to_params(golden["args"])), input_path=inp,
+                               device=local)
+    s_outs = sorted((os.path.join(work, fn) for fn in os.listdir(work) if fn.startswith("two.silver")),
+                    key=lambda p: (len(p), p))
+    result["two_stage"] = {"silver": pu.digest_outputs(s_outs),
+                           "golden": pu.digest_outputs([pg + ".fa"])}
+    dist.barrier()
+
+    # ---- slice mode: this rank is handed only its own records of the input (cut at a record
+    # boundary); no output files, the record digest is put together from the ranks' parts ----
+    starts = [0]
+    pos, line = 0, 0
+    while True:
+        nl = fq.find(b"\n", pos)
+        if nl < 0:
+            break
+        pos = nl + 1
+        line += 1
+        if line % 4 == 0 and pos < len(fq):
+            starts.append(pos)
+    n_rec = len(starts)
+    cut = [starts[n_rec * r // world] if r < world else len(fq) for r in range(world + 1)]
+    mine = fq[cut[rank]:cut[rank + 1]]
+    kw_s = dict(_args_to_params(silver["args"]), fastq_offset=cut[rank], fastq_total=len(fq))
+    kw_g = _args_to_params(golden["args"])
+    r1 = grb.run_path(mine, input_path="(slice)", write_outputs=False, device=local, **kw_s)
+    ss, sg = grb.run_two_stage(mine, kw_s, kw_g, input_path="(slice)", device=local,
+                               write_outputs=False)
+    result["slice"] = {"bytes": len(mine), "digest": r1.out_digest, "expect": rs.out_digest,
+                       "selected": r1.reads_selected, "expect_selected": rs.reads_selected,
+                       "two_silver": ss.out_digest, "two_golden": sg.out_digest,
+                       "expect_golden": rg.out_digest, "golden_reads": sg.num_reads,
+                       "expect_golden_reads": rg.num_reads}
+    dist.barrier()
+
     grb.api.comm_destroy()
     with open(os.path.join(out_dir, f"result{rank}.json"), "w") as f:
         json.dump(result, f)

@@ -51,3 +51,11 @@ def test_sharded_run_matches_reference_fixtures(world, tmp_path):
             stats = dict((k, v) for k, v in g["stats"] if k in ("m_filterSize:", "num_passed_reads:"))
             assert r["cases"][name]["filter_bits"] == stats["m_filterSize:"]
             assert r["cases"][name]["num_passed_reads"] == stats["num_passed_reads:"]
+        # grb_run_two_stage with the ingest sharded over the ranks: the reference's files
+        assert r["two_stage"]["silver"] == golden["silver_default"]["outputs"]
+        assert r["two_stage"]["golden"] == golden["golden_default"]["outputs"]
+        # slice mode: each rank saw only its own records of the input
+        sl = r["slice"]
+        assert 0 < sl["bytes"] and sl["digest"] == sl["expect"] and sl["selected"] == sl["expect_selected"]
+        assert sl["two_silver"] == sl["expect"] and sl["two_golden"] == sl["expect_golden"]
+        assert sl["golden_reads"] == sl["expect_golden_reads"]

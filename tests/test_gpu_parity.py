@@ -529,3 +529,47 @@ def test_cfg2_full_size_is_independent_of_batching_and_fill_path(monkeypatch):
     assert key(a) == key(b)
     assert a.num_reads == 120000 and a.reads_selected > 20000 and a.paths in (5, 6)
     assert a.pop < a.filter_bits and a.bases_pass2 == a.reads_visited * 25000
+
+
+# ---- full-size reference digests (tests/golden/full_size.json, made by make_full_size.py) ---------
+def _full_size():
+    import json
+    with open(os.path.join(pu.ROOT, "tests", "golden", "full_size.json")) as f:
+        return json.load(f)
+
+
+def _stats_dict(stats, which):
+    """Last value of each --verbose counter of parse_stats (the final path's running totals)."""
+    out = {}
+    for k, v in stats:
+        out[k] = v
+    return out[which]
+
+
+@pytest.mark.parametrize("cfg", ["cfg1", "cfg2"])
+def test_full_size_config_matches_reference_digests(cfg):
+    """BASELINE.json configs[0] and configs[1] at their own size: both launches of one assembly
+    (silver run, golden run on the concatenated silver paths, bin/goldrush:240-260) through
+    grb_run_two_stage on a host FASTQ buffer, against what the reference's own sources wrote for the
+    same input: record digest of all output files, record and byte counts, filter size, and the
+    number of reads that passed pass 1."""
+    fs = _full_size()[cfg]
+    s = fs["synth"]
+    sp = grb.api.synth_params(s["genome"], float(s["cov"]), s["read_len"], s["seed"])
+    ptr, n = grb.synth_fastq_raw(sp)
+    assert n == fs["input_bytes"], "generator drifted from the fixture"
+    common = dict(kmer_size=22, weight=16, hash_num=3, tile_length=1000, block_size=10,
+                  unassigned_min=5, assigned_max=1, occupancy=0.1, threshold=10, phred_delta=5,
+                  ratio=0.9, genome_size=s["genome"], phred_min=fs["phred_min"], seed_preset=SEED22)
+    try:
+        rs, rg = grb.run_two_stage(ptr, dict(common, max_paths=5, min_length=20000, silver_path=1),
+                                   dict(common, min_length=0, silver_path=0), nbytes=n,
+                                   input_path="(memory)", write_outputs=False)
+    finally:
+        grb.free_host(ptr)
+    for res, ref in ((rs, fs["silver"]), (rg, fs["golden"])):
+        assert res.out_digest == ref["out_digest"]
+        assert res.reads_selected == ref["records"]
+        assert res.filter_bits == _stats_dict(ref["stats"], "m_filterSize:")
+        assert res.num_passed_reads == _stats_dict(ref["stats"], "num_passed_reads:")
+    assert rg.num_reads == rs.reads_selected
