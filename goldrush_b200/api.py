@@ -128,6 +128,8 @@ def lib():
         "grb_calc_optimal_size": (u64, [u64, C.c_uint, dbl]),
         "grb_default_hash_universe": (u64, [u64, u64, u64]),
         "grb_phred_finalize": (None, [dbl, dbl, u64, P(u32), P(u32)]),
+        "grb_phred_finalize_batch": (None, [vp, u64, vp, vp]),
+        "grb_query_sharded": (i32, [vp]),
         "grb_create": (i32, [P(Params), P(vp)]),
         "grb_destroy": (None, [vp]),
         "grb_last_error": (C.c_char_p, [vp]),

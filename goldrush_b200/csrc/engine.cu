@@ -811,6 +811,12 @@ grb_comm_info(const grb_ctx* c, int* rank, int* world)
 }
 
 int
+grb_query_sharded(const grb_ctx* c)
+{
+  return c->comm && c->shard_query ? 1 : 0;
+}
+
+int
 grb_profile_enable(grb_ctx* c, int on)
 {
   cudaSetDevice(c->device);

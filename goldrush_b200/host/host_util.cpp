@@ -82,4 +82,15 @@ grb_phred_finalize(double first_half_sum, double total_sum, uint64_t n, uint32_t
   *delta = (uint32_t)abs((int32_t)(-10 * log10(first_avg)) - (int32_t)(-10 * log10(second_avg)));
 }
 
+// the same for n reads at once (host threads), from the metadata K1 returned
+void
+grb_phred_finalize_batch(const grb_read_meta* meta, uint64_t n, uint32_t* avg, uint32_t* delta)
+{
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {
+    grb_phred_finalize(meta[i].phred_first_half_sum, meta[i].phred_total_sum, meta[i].qual_len,
+                       &avg[i], &delta[i]);
+  }
+}
+
 } // extern "C"

@@ -108,6 +108,9 @@ typedef struct grb_read_meta
                          the key of filter_out_reads, goldrush_path.cpp:266-299,919-932) */
 } grb_read_meta;
 
+/* grb_phred_finalize for n reads at once, from the metadata K1 returned (host threads) */
+void grb_phred_finalize_batch(const grb_read_meta* meta, uint64_t n, uint32_t* avg, uint32_t* delta);
+
 /* Decodes every complete 4-line record in bytes[0, n) and appends it to the read store.
  * *consumed = bytes used; re-send the tail with the next chunk (final != 0: a last record without
  * trailing newline is accepted).  bytes is HOST memory (pageable or pinned). */
@@ -248,6 +251,8 @@ void grb_comm_destroy(void);
 int grb_bitvector_or_reduce(grb_ctx* ctx);
 /* ctx == NULL: the process-wide communicator; else what this context uses (0 / 1 if unsharded) */
 int grb_comm_info(const grb_ctx* ctx, int* rank, int* world);
+/* 1 if this context shards each batch's speculative query over the ranks, else 0 */
+int grb_query_sharded(const grb_ctx* ctx);
 /* Host-side all-gather of variable-length byte strings through the context's communicator (staged
  * through device memory): rank r contributes send[0, n); out (caller-allocated, capacity out_cap)
  * receives the strings of ranks 0..W-1 back to back, sizes[r] = bytes of rank r.  A context
