@@ -1,5 +1,6 @@
-# Non-meson build of goldrush-b200 (meson is not installed in the build image; the meson.build
-# files next to the sources describe the same targets for a reference checkout).
+# Non-meson build of goldrush-b200 (meson is not installed in the build image; meson.build,
+# goldrush_b200/meson.build and goldrush_path/meson.build describe the same targets for a reference
+# checkout, and tests/test_host_logic.py keeps the two descriptions in step).
 #
 #   make            libgoldrush_b200.so (CUDA, sm_100a) + goldrush-path + grb-synth
 #   make oracle     CPU checkers under oracle/ (test infrastructure)

@@ -189,6 +189,32 @@ def test_no_product_source_touches_the_oracle():
     assert "oracle" not in lib_rule
 
 
+def test_meson_files_name_the_sources_the_makefile_builds():
+    """meson is not installed in the build image, so the meson.build files cannot be run here; what
+    can be checked is that they describe the same build: every file they name exists, and every
+    kernel header / host source the Makefile compiles is named."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for rel in ("meson.build", "goldrush_b200/meson.build", "goldrush_path/meson.build"):
+        assert os.path.exists(os.path.join(root, rel)), rel
+    with open(os.path.join(root, "goldrush_b200", "meson.build")) as f:
+        lib_meson = f.read()
+    named = set(re.findall(r"'((?:csrc|host|\.\./include)/[^']+)'", lib_meson))
+    for n in named:
+        assert os.path.exists(os.path.join(root, "goldrush_b200", n)), n
+    csrc = {"csrc/" + f for f in os.listdir(os.path.join(root, "goldrush_b200", "csrc"))}
+    assert csrc <= named, csrc - named
+    with open(os.path.join(root, "Makefile")) as f:
+        mk = f.read()
+    host_lib = set(re.findall(r"goldrush_b200/(host/\w+\.cpp)", mk.split("HOST_LIB_SRC :=")[1].split("\n")[0]))
+    assert host_lib and host_lib <= named, host_lib - named
+    assert "arch=compute_100a,code=sm_100a" in lib_meson and "arch=compute_100a,code=sm_100a" in mk
+    with open(os.path.join(root, "goldrush_path", "meson.build")) as f:
+        exe = f.read()
+    assert "executable('goldrush-path'" in exe and "install : true" in exe
+    for n in re.findall(r"'\.\./(goldrush_b200/host/[^']+)'", exe):
+        assert os.path.exists(os.path.join(root, n)), n
+
+
 def test_synth_generator_is_deterministic_and_thread_independent():
     sp = grb.api.synth_params(50000, 3.0, 2000, 77)
     a = grb.synth_fastq(sp)
