@@ -61,14 +61,6 @@ grb_norm_id(uint32_t v)
   return v > GRB_SAT_MASK ? (v & ~GRB_SAT_MASK) : v; // goldrush_path.cpp:574-583
 }
 
-__global__ void
-k_batch_begin(GrbSelState* __restrict__ state)
-{
-  if (!state->halt) {
-    state->batch_inserts = 0;
-  }
-}
-
 __device__ __forceinline__ void
 grb_vote_add(uint32_t* keys, uint32_t* counts, uint32_t tmask, uint32_t id, uint32_t delta)
 {

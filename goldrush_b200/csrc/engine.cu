@@ -276,6 +276,7 @@ struct grb_ctx
   // ordered commit (kernels_commit.cuh)
   bool b3_attr = false, b3_stage_attr = false;
   uint32_t b3_ctas = 0, b3_dcap = 0;
+  uint32_t b3_bs = 512; // threads per CTA of k3_fix: 512, or 256 (two CTAs per SM; measured slower)
   uint64_t b3_cap_tiles = 0, b3_cmat_cap = 0;
   DevBuf<GrbShared3> b3_shared;
   DevBuf<uint32_t> b3_bm, b3_cand, b3_ix_cnt;
@@ -285,6 +286,7 @@ struct grb_ctx
   DevBuf<GrbReadPlan> b3_np;
   DevBuf<GrbFixCtl> b3_ctl;
   DevBuf<unsigned long long> b3_d_keys, b3_barrier;
+  DevBuf<uint32_t> b3_dbg; // GRB_FIX_DEBUG=<file>: per-read records of the commit's re-validation phase
 
   // ---- multi-GPU (comm.cuh): the process-wide NCCL communicator, when this context's device is
   // the one it was created on and it spans more than one rank ----
@@ -685,6 +687,16 @@ grb_destroy(grb_ctx* c)
   }
   if (c->up_host) {
     grb_arena_give(c->up_host);
+  }
+  if (c->b3_dbg.p && getenv("GRB_FIX_DEBUG")) {
+    std::vector<uint32_t> h(c->b3_dbg.cap);
+    if (cudaMemcpy(h.data(), c->b3_dbg.p, h.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (FILE* f = fopen(getenv("GRB_FIX_DEBUG"), "wb")) {
+        const size_t n = std::min<size_t>(h[0], (h.size() - 4) / 4);
+        fwrite(h.data(), 4, 4 + 4 * n, f);
+        fclose(f);
+      }
+    }
   }
   grb_pool_free(c->filt.blocks);
   grb_pool_free(c->filt.slots);
@@ -2062,6 +2074,7 @@ sel_prepare(grb_ctx* c, uint64_t max_len)
     }
     q.sw_words = (uint32_t)((T + k + 63) / 32 + 4);
     q.silver = c->p.silver_path;
+    q.pad = 0;
     q.threshold = c->p.threshold;
     q.unassigned_min = c->p.unassigned_min;
     q.assigned_max = c->p.assigned_max;
@@ -2256,18 +2269,32 @@ batch3_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
   if (!c->b3_attr) {
     GRB_CUDA(c, cudaFuncSetAttribute(k3_fix<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)c->b2_smem_max));
+    GRB_CUDA(c, cudaFuncSetAttribute(k3_fix<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)c->b2_smem_max));
     int per_sm = 0;
     GRB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_fix<512>, 512,
                                                               c->b2_smem_max));
     if (per_sm < 1) {
       return c->fail(GRB_ERR_CUDA, "k3_fix cannot be resident on this device");
     }
-    c->b3_ctas = (uint32_t)c->sm_count;
+    // The re-validation phase of the commit is one CTA per read.  GRB_FIX_BS=256 runs two
+    // 256-thread CTAs per SM (one read each) instead of one 512-thread CTA per SM (two reads in
+    // turn): measured slower on cfg2 (commit 82 -> 108 ms), because a batch waits for its slowest
+    // read and that read takes twice as long with half the threads.  Per-CTA scratch is sized for
+    // two CTAs per SM either way.
+    if (const char* e = getenv("GRB_FIX_BS")) {
+      c->b3_bs = strcmp(e, "256") == 0 ? 256u : 512u;
+    }
+    c->b3_ctas = (uint32_t)c->sm_count * 2;
     c->b3_dcap = (uint32_t)next_pow2(4 * T * h + 64);
     GRB_CUDA(c, c->b3_d_keys.reserve((size_t)c->b3_ctas * c->b3_dcap, 0, s));
     GRB_CUDA(c, c->b3_d_vals.reserve((size_t)c->b3_ctas * c->b3_dcap, 0, s));
     GRB_CUDA(c, c->b3_ctl.reserve(1, 0, s));
     GRB_CUDA(c, c->b3_barrier.reserve(1, 0, s));
+    if (getenv("GRB_FIX_DEBUG")) {
+      GRB_CUDA(c, c->b3_dbg.reserve_exact((size_t)4 + 4 * (1u << 21), s));
+      GRB_CUDA(c, cudaMemsetAsync(c->b3_dbg.p, 0, 16, s));
+    }
     c->b3_attr = true;
   }
   if (max_batch_tiles > c->b3_cap_tiles) {
@@ -2369,6 +2396,8 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   b3.d_vals = c->b3_d_vals.p;
   b3.cmat_g = c->b3_cmat_g.p;
   b3.barrier = c->b3_barrier.p;
+  b3.dbg = c->b3_dbg.p;
+  b3.dbg_cap = c->b3_dbg.p ? (uint32_t)((c->b3_dbg.cap - 4) / 4) : 0u;
 
   const uint32_t n_cap = std::max<uint32_t>(b.max_tiles, 1);
   const uint32_t us = (uint32_t)next_pow2(2 * (uint64_t)n_cap);
@@ -2376,21 +2405,28 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   const size_t as_pad = ((size_t)(n_cap + 15) / 16) * 16;
   const size_t cmat_smem = (size_t)6 * n_cap * 4 + 8 + (size_t)2 * us * 4 + as_pad +
                            (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
-  const uint32_t dc = kFixDeltaSmem;
-  const size_t fix_smem = (size_t)dc * 12 + (size_t)n_cap * 8 + ((size_t)2 * us + (size_t)8 * n_cap + 2) * 4 +
-                          as_pad + (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
+  // delta table of the re-validation phase: 8192 entries (GRB_FIX_DELTA=16384 doubles it when the
+  // batch's longest read leaves room; measured slower on cfg2, commit 76 -> 84 ms: clearing and
+  // scanning the table costs every read more than the shorter probe sequences save the few full ones)
+  uint32_t dc = kFixDeltaSmem;
+  if (const char* e = getenv("GRB_FIX_DELTA")) {
+    dc = strcmp(e, "16384") == 0 ? 2 * kFixDeltaSmem : kFixDeltaSmem;
+  }
+  auto fix_bytes = [&](uint32_t d) {
+    return (size_t)d * 12 + (size_t)n_cap * 8 + ((size_t)2 * us + (size_t)8 * n_cap + 2) * 4 + as_pad +
+           (cm_smem ? (size_t)n_cap * n_cap * 4 : 0);
+  };
+  if (fix_bytes(dc) > c->b2_smem_max) {
+    dc = kFixDeltaSmem;
+  }
+  const size_t fix_smem = fix_bytes(dc);
   if (cmat_smem > c->b2_smem_max || fix_smem > c->b2_smem_max) {
     return c->fail(GRB_ERR_ARG, "a read spans too many tiles for the commit kernel's shared "
                                 "memory: raise the tile length");
   }
-  GRB_CUDA(c, cudaMemsetAsync(b3.bm, 0, (size_t)bm_bits / 8, s));
-  GRB_CUDA(c, cudaMemsetAsync(b3.fbits, 0, ((uint64_t)b.n_bt * T / 32 + 2) * 4, s));
-  GRB_CUDA(c, cudaMemsetAsync(b3.counters, 0, 32, s));
-  GRB_CUDA(c, cudaMemsetAsync(b3.fl_n, 0, (size_t)b.nb * 4, s));
-  GRB_CUDA(c, cudaMemsetAsync(b3.plan_out, 0, (size_t)b.nb * sizeof(GrbReadPlan), s));
-  GRB_CUDA(c, cudaMemsetAsync(b3.ctl, 0, sizeof(GrbFixCtl), s));
-  GRB_CUDA(c, cudaMemsetAsync(b3.barrier, 0, 8, s));
-  k_batch_begin<<<1, 1, 0, s>>>(c->d_state);
+  static_assert(sizeof(GrbReadPlan) % 16 == 0 && sizeof(GrbFixCtl) == 16, "k3_reset stores uint4");
+  k3_reset<<<(unsigned)c->sm_count * 4, 256, 0, s>>>(b3, c->d_state, bm_bits / 32,
+                                                     (uint32_t)((uint64_t)b.n_bt * T / 32 + 2), b.nb);
   c->launches += 1;
   if (!c->comm || !c->shard_query) {
     c->kbegin();
@@ -2469,8 +2505,17 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
     uint32_t us_a = us, n_cap_a = n_cap, dc_a = dc, cm_a = cm_smem;
     void* args[] = { &reads, &c->prm, &bd, &b3, &st, &dec, &dec_idx, &us_a, &n_cap_a, &dc_a, &cm_a };
     c->kbegin();
-    GRB_CUDA(c, cudaLaunchCooperativeKernel((void*)k3_fix<512>, dim3(c->b3_ctas), dim3(512), args,
-                                            fix_smem, s));
+    int per_sm = 1;
+    if (c->b3_bs == 256) {
+      GRB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k3_fix<256>, 256, fix_smem));
+    }
+    if (c->b3_bs == 256 && per_sm >= 2) {
+      GRB_CUDA(c, cudaLaunchCooperativeKernel((void*)k3_fix<256>, dim3(2 * c->sm_count), dim3(256), args,
+                                              fix_smem, s));
+    } else {
+      GRB_CUDA(c, cudaLaunchCooperativeKernel((void*)k3_fix<512>, dim3(c->sm_count), dim3(512), args,
+                                              fix_smem, s));
+    }
     c->kend(GRB_K_COMMIT);
   }
   c->kbegin();
@@ -2523,7 +2568,16 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
     const uint64_t fit = c->p.genome_size / (2 * max_len);
     batch_reads = (uint32_t)std::min<uint64_t>(batch_reads, std::max<uint64_t>(32, fit));
   }
-  const uint64_t kChunk = c->batch_mode ? 4ull * batch_reads : 256;
+  // batches queued between two looks at the loop state (path rollover / exit): after a rollover
+  // the rest of the chunk's launches return at once (state->halt) and the chunk is re-planned from
+  // the read after it, so a longer chunk trades a few empty launches per rollover (five per run)
+  // for fewer host round trips (35 -> 9 per cfg2 run)
+  static const uint64_t chunk_batches = [] {
+    const char* e = getenv("GRB_CHUNK_BATCHES");
+    const long v = e ? strtol(e, nullptr, 10) : 0;
+    return (uint64_t)(v > 0 && v <= 1024 ? v : 8);
+  }();
+  const uint64_t kChunk = c->batch_mode ? chunk_batches * batch_reads : 256;
   while (i < end && !c->sel_finished) {
     uint64_t launched = 0, j = i;
     if (c->batch_mode) {

@@ -83,6 +83,8 @@ struct GrbB3
   int32_t* d_vals;
   uint32_t* cmat_g;             // [n_cta * n_cap^2] when the count matrix does not fit shared memory
   unsigned long long* barrier;  // grid barrier counter, zero at launch
+  uint32_t* dbg;                // GRB_FIX_DEBUG: [0] cursor, then 4-word records per re-validated read
+  uint32_t dbg_cap;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -106,6 +108,39 @@ struct GrbB3
 #define GRB_CTR_MEMBER 2 // member cursor
 #define GRB_CTR_CAND 3   // candidates of k3_mark
 #define GRB_CTR_LISTED 4 // probes listed by k3_members
+
+// start of a batch: everything the index and the commit expect zeroed, in one launch (it was eight
+// memsets and a one-thread kernel: launch gaps were 5 % of the step)
+__global__ void __launch_bounds__(256)
+k3_reset(GrbB3 b3, GrbSelState* __restrict__ state, uint32_t bm_words, uint32_t fb_words, uint32_t nb)
+{
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  uint4* bm4 = reinterpret_cast<uint4*>(b3.bm);
+  for (uint32_t i = tid; i < bm_words / 4; i += nth) {
+    bm4[i] = z;
+  }
+  for (uint32_t i = tid; i < fb_words; i += nth) {
+    b3.fbits[i] = 0u;
+  }
+  uint4* po = reinterpret_cast<uint4*>(b3.plan_out);
+  for (uint32_t i = tid; i < nb * (uint32_t)(sizeof(GrbReadPlan) / 16); i += nth) {
+    po[i] = z;
+  }
+  for (uint32_t i = tid; i < nb; i += nth) {
+    b3.fl_n[i] = 0u;
+  }
+  if (tid < 8) {
+    b3.counters[tid] = 0u;
+  }
+  if (tid == 8) {
+    *reinterpret_cast<uint4*>(b3.ctl) = z;
+    *b3.barrier = 0ull;
+    if (!state->halt) {
+      state->batch_inserts = 0;
+    }
+  }
+}
 
 // append `item` (when `take`) to a global list with one atomic per CTA round
 __device__ __forceinline__ void
@@ -673,7 +708,7 @@ grb3_walk(const GrbB3& b3, uint32_t B, uint32_t n_commit)
 
 // F: one read under the ids its conflict frames see now.  Whole CTA.
 template<int BS>
-__device__ __forceinline__ void
+__device__ __forceinline__ uint32_t
 grb3_read(const GrbReadsDev& reads, const GrbSelParams& prm, const GrbBatchDev& bd, const GrbB3& b3,
           const GrbFixSmem& sm, uint32_t b, uint32_t us, uint32_t dc, uint32_t cm_smem, uint32_t n_cap)
 {
@@ -869,11 +904,74 @@ grb3_read(const GrbReadsDev& reads, const GrbSelParams& prm, const GrbBatchDev& 
     pass_b(d_light);
     __syncthreads();
     if (s_any_rescan) {
-      for (uint32_t t = 0; t < n; ++t) {
-        if (sm.rescan[t]) {
-          rescan_tile(t, d_light);
+      // full arg-max of every flagged tile over base counts + deltas, all flagged tiles at once:
+      // the vote tables of the flagged tiles are walked as one flat range by the whole CTA, four
+      // independent loads in flight per thread (every dependent round trip to L2 costs ~700
+      // cycles: one tile after the other with two barriers each was what reads overlapping an
+      // inserted read spent 36 000 cycles on), then the ids only the delta table knows are added
+      __shared__ uint32_t s_nflag;
+      if (threadIdx.x == 0) {
+        uint32_t nf = 0;
+        for (uint32_t t = 0; t < n; ++t) {
+          if (sm.rescan[t]) {
+            sm.nbest[t] = 0;
+            sm.root[nf++] = t;
+          }
+        }
+        s_nflag = nf;
+      }
+      __syncthreads();
+      const uint32_t total = s_nflag * vts; // vts is a power of two >= 32: a warp never straddles tiles
+      for (uint32_t base = threadIdx.x; base < total; base += 4 * BS) {
+        uint32_t ids[4], cs[4], ts[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t idx = base + u * BS;
+          ids[u] = 0;
+          cs[u] = 0;
+          ts[u] = 0;
+          if (idx < total) {
+            ts[u] = sm.root[idx / vts];
+            const uint64_t at = (uint64_t)(bt0 + ts[u]) * vts + (idx & vmask);
+            ids[u] = __ldg(&b3.vk[at]);
+            cs[u] = __ldg(&b3.vc[at]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          unsigned long long best = 0;
+          if (ids[u]) {
+            best = grb2_pack_best(cs[u] + (uint32_t)d_light.get(ts[u], ids[u]), ids[u]);
+          }
+          if (__any_sync(0xffffffffu, base + u * BS < total)) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+              const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, d);
+              best = o > best ? o : best;
+            }
+            if ((threadIdx.x & 31) == 0 && best) {
+              atomicMax(&sm.nbest[ts[u]], best);
+            }
+          }
         }
       }
+      for (uint32_t i = threadIdx.x; i <= d_light.mask; i += BS) {
+        const unsigned long long key = d_light.keys[i];
+        if (key == GRB_DK_EMPTY || d_light.vals[i] <= 0) {
+          continue;
+        }
+        const uint32_t t = (uint32_t)(key >> 32), id = (uint32_t)key;
+        if (!sm.rescan[t]) {
+          continue;
+        }
+        const uint32_t c = grb2_vote_get(b3.vk + (uint64_t)(bt0 + t) * vts, b3.vc + (uint64_t)(bt0 + t) * vts,
+                                         vmask, id) + (uint32_t)d_light.vals[i];
+        const unsigned long long pk = grb2_pack_best(c, id);
+        if (pk) {
+          atomicMax(&sm.nbest[t], pk);
+        }
+      }
+      __syncthreads();
     }
   } else {
     // too many distinct (tile, id) pairs for shared memory: one tile at a time in global scratch
@@ -963,6 +1061,7 @@ grb3_read(const GrbReadsDev& reads, const GrbSelParams& prm, const GrbBatchDev& 
     __stcg(&b3.np_dh[b], s_dh);
   }
   __syncthreads();
+  return (heavy ? 1u : 0u) | (s_changed ? 2u : 0u) | (s_uchg ? 4u : 0u) | (s_any_rescan ? 8u : 0u);
 }
 
 // One persistent cooperative launch per batch.  dec_idx[b] = index of read b in `decisions`.
@@ -972,7 +1071,7 @@ grb3_read(const GrbReadsDev& reads, const GrbSelParams& prm, const GrbBatchDev& 
 // prof[] (GrbSelState): 0 walk, 2 reads, 3 order scan, 4 final (SM cycles of CTA 0); 1 plans that
 // differed from the assumed ones, 5 conflict frames, 6 reads, 7 iterations, 8 inserts, 9 batches.
 template<int BS>
-__global__ void __launch_bounds__(BS, 1)
+__global__ void __launch_bounds__(BS, 512 / BS)
 k3_fix(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3, GrbSelState* __restrict__ state_g,
        grb_decision* __restrict__ decisions, const uint64_t* __restrict__ dec_idx, uint32_t us,
        uint32_t n_cap, uint32_t dc, uint32_t cm_smem)
@@ -1122,7 +1221,18 @@ k3_fix(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3, GrbSelStat
         }
         continue;
       }
-      grb3_read<BS>(reads, prm, bd, b3, sm, b, us, dc, cm_smem, n_cap);
+      const long long c0 = clock64();
+      const uint32_t fl = grb3_read<BS>(reads, prm, bd, b3, sm, b, us, dc, cm_smem, n_cap);
+      if (b3.dbg && threadIdx.x == 0) {
+        const uint32_t at = atomicAdd(&b3.dbg[0], 1u);
+        if (at < b3.dbg_cap) {
+          uint32_t* rec = b3.dbg + 4 + 4 * (size_t)at;
+          rec[0] = b | (iters << 12) | (fl << 16) | ((uint32_t)st.prof[9] << 20);
+          rec[1] = __ldcg(&b3.fl_n[b]);
+          rec[2] = (uint32_t)(clock64() - c0);
+          rec[3] = cta;
+        }
+      }
     }
     GRB_TICK(2)
     grb_grid_barrier(b3.barrier, ++phase * n_cta);
@@ -1161,49 +1271,79 @@ k3_fix(GrbReadsDev reads, GrbSelParams prm, GrbBatchDev bd, GrbB3 b3, GrbSelStat
     d.num_assigned = g_a[b];
     decisions[dec_idx[b]] = d;
   }
-  if (threadIdx.x == 0) {
-    GrbSelState& s = st;
-    uint64_t conflict_frames = 0;
-    for (uint32_t b = 0; b < n_commit; ++b) {
+  // The counters of the committed reads are sums; the one order-dependent event, the path rollover
+  // (silver_path_check, goldrush_path.cpp:167-186), can only happen at the last committed read: the
+  // order scan cut the batch there (s_rolled).
+  __shared__ unsigned long long s_acc[9];
+  if (threadIdx.x < 9) {
+    s_acc[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  {
+    unsigned long long a[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    for (uint32_t b = threadIdx.x; b < n_commit; b += BS) {
       const GrbReadPlan p = g_np[b];
       const uint32_t n = bd.tile_first[b + 1] - bd.tile_first[b];
       const uint32_t n_as = g_a[b];
       const int dh = g_b[b];
-      s.cur.queries += g_c[3 * b];
-      s.cur.hits += (uint64_t)((int64_t)g_c[3 * b + 1] + dh);
-      s.cur.misses += (uint64_t)((int64_t)g_c[3 * b + 2] - dh);
-      s.cur.total_tiles += n;
-      s.cur.assigned_tiles += n_as;
-      s.cur.unassigned_tiles += n - n_as;
-      conflict_frames += b3.fl_n[b];
+      a[0] += g_c[3 * b];
+      a[1] += (unsigned long long)((long long)g_c[3 * b + 1] + dh);
+      a[2] += (unsigned long long)((long long)g_c[3 * b + 2] - dh);
+      a[3] += n;
+      a[4] += n_as;
+      a[5] += __ldcg(&b3.fl_n[b]);
       if (p.verdict == GRB_UNTRIMMED || p.verdict == GRB_TRIMMED) {
-        s.cur.inserted_bases += p.out_bases;
-        s.cur.num_reads_in_path += 1;
-        s.batch_inserts += 1;
-        s.prof[8] += p.n_blocks != 0 ? 1 : 0;
-        if (prm.silver && prm.target_bases < s.cur.inserted_bases) { // silver_path_check, :167-186
-          const uint64_t read_idx = bd.read_idx[b];
-          s.snap = s.cur;
-          s.snap.rollover_read = read_idx;
-          s.n_snap = 1;
-          s.curr_path += 1;
-          s.halt = 1;
-          s.halt_read = read_idx;
-          if (prm.max_paths < s.curr_path) {
-            s.finished = 1;
-          } else {
-            s.cur.inserted_bases = 0;
-            s.cur.num_reads_in_path = 0;
-            s.cur.phred_sum_in_path = 0;
-          }
-        }
+        a[6] += p.out_bases;
+        a[7] += 1;
+        a[8] += p.n_blocks != 0 ? 1 : 0;
       }
-      if (!s.finished) {
-        s.cur.valid_reads += 1;
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        a[q] += __shfl_xor_sync(0xffffffffu, a[q], d);
+      }
+      if ((threadIdx.x & 31) == 0 && a[q]) {
+        atomicAdd(&s_acc[q], a[q]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    GrbSelState& s = st;
+    s.cur.queries += s_acc[0];
+    s.cur.hits += s_acc[1];
+    s.cur.misses += s_acc[2];
+    s.cur.total_tiles += s_acc[3];
+    s.cur.assigned_tiles += s_acc[4];
+    s.cur.unassigned_tiles += s_acc[3] - s_acc[4];
+    s.cur.inserted_bases += s_acc[6];
+    s.cur.num_reads_in_path += s_acc[7];
+    s.batch_inserts += (uint32_t)s_acc[7];
+    s.prof[8] += s_acc[8];
+    s.cur.valid_reads += n_commit;
+    if (n_commit && prm.silver && prm.target_bases < s.cur.inserted_bases) {
+      const uint32_t b = n_commit - 1; // the read whose insertion closed the path
+      const uint64_t read_idx = bd.read_idx[b];
+      s.snap = s.cur;
+      s.snap.valid_reads -= 1; // the reference counts the closing read after the snapshot (:1089)
+      s.snap.rollover_read = read_idx;
+      s.n_snap = 1;
+      s.curr_path += 1;
+      s.halt = 1;
+      s.halt_read = read_idx;
+      if (prm.max_paths < s.curr_path) {
+        s.finished = 1;
+        s.cur.valid_reads -= 1; // exit(0) inside silver_path_check: the closing read is never counted
+      } else {
+        s.cur.inserted_bases = 0;
+        s.cur.num_reads_in_path = 0;
+        s.cur.phred_sum_in_path = 0;
       }
     }
     s.ids_inserted = (s.halt == 1 && !s.finished) ? 0u : s_ids_end;
-    s.prof[5] += conflict_frames;
+    s.prof[5] += s_acc[5];
     s.prof[6] += n_commit;
     s.prof[7] += iters;
     s.prof[9] += 1;

@@ -189,7 +189,7 @@ def test_probe_microbenchmark_builds_the_filter_it_claims():
             assert abs(r.pop / r.filter_bits - 0.3) < 0.005
             assert r.probes == ((1 << 20) // h) * h and r.query_ms > 0 and r.insert_ms > 0
             assert r.checksum > 0 and r.probes_missed == 0
-            assert r.footprint_bytes == ((r.filter_bits + 191) // 192) * 32 + (r.pop + 1) * 16
+            assert r.footprint_bytes == ((r.filter_bits + 191) // 192) * 32 + (r.pop + 1) * 8  # 8-byte {id, count} slots
 
 
 def _tile_hashes(seq, t, T, k, seeds):

@@ -1,0 +1,17 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_g.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_g.log
+tail -3 gpurun_out/pytest_g.log
+for dl in 16384 8192; do
+GRB_FIX_DELTA=$dl GRB_BENCH_SKIP_CPU=1 timeout 600 python bench.py --workload cfg2 --steps 5 --warmup 3 > gpurun_out/bench_g_cfg2_dl$dl.json 2> gpurun_out/bench_g_cfg2_dl$dl.err; echo "cfg2 dl=$dl rc=$?"
+done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/bench_g_*.json")):
+    try:
+        d=json.load(open(f))
+        print(f, "ms/step", round(d["ms_per_step"],1), "e2e_s", round(d["e2e"]["s_per_step"],3), "parity", d["parity_digest_ok"], "launches", d["gpu_launches"])
+        print("  kernels", {k: round(v,1) for k,v in d["kernels_ms_per_step"].items()}, d["commit_profile_last_step"])
+    except Exception as e:
+        print(f, "failed", e)
+PY
