@@ -9,12 +9,16 @@ one assembly exactly as bin/goldrush:240-260 issues them -- the --silver_path ru
 and the two must agree byte for byte.  Committed per stage: md5 of every output file, the
 order-sensitive record digest (oracle/_build/grb-digest = grb_run_result.out_digest), the
 --verbose counters, and the reference's own phase timers (seconds on the authoring container's 8
-cores).  cfg3 is produced with the port only (the reference needs ~4x longer); say so in `by`.
+cores).  cfg3 (1 Gbp) and cfg4 (3 Gbp) cannot be produced in the authoring container: at 1 Gbp the
+reference's m_data + m_counts alone are 8 bytes x up to 6.4e9 set bits = 51 GB next to a 3.3 GB
+bit vector, its rank structure and the 60 GB input, on a box with 62 GB of RAM (the attempt was
+killed by the kernel's OOM handler; the port, which also holds the input in memory, even earlier).
+Parity at those sizes rests on size-independent properties instead (tests/test_gpu_parity.py,
+bench.py: batch engine == one-read-at-a-time engine, any batch size, any number of GPUs).
 
 Run in the authoring container only (needs /root/reference for oracle/_ref):
     python tests/golden/make_full_size.py cfg1 cfg2 [--work DIR] [--keep]
-    python tests/golden/make_full_size.py cfg3 --port-only
-cfg1: ~1.5 min, cfg2: ~45 min (reference 25 + port 15), cfg3 (port only): hours.
+cfg1: ~1.5 min, cfg2: ~45 min (reference 25 + port 15).
 """
 import argparse
 import json
@@ -37,7 +41,6 @@ COMMON = ["-k", "22", "-w", "16", "-s", S, "-h", "3", "-t", "1000", "-b", "10", 
 CONFIGS = {
     "cfg1": dict(genome=5_000_000, cov=25, read_len=20000, seed=1001, phred_min=0, g="5e6"),
     "cfg2": dict(genome=100_000_000, cov=30, read_len=25000, seed=1002, phred_min=20, g="1e8"),
-    "cfg3": dict(genome=1_000_000_000, cov=30, read_len=20000, seed=1003, phred_min=20, g="1e9"),
 }
 
 
