@@ -573,3 +573,37 @@ def test_full_size_config_matches_reference_digests(cfg):
         assert res.filter_bits == _stats_dict(ref["stats"], "m_filterSize:")
         assert res.num_passed_reads == _stats_dict(ref["stats"], "num_passed_reads:")
     assert rg.num_reads == rs.reads_selected
+
+
+def test_reads_of_hundreds_of_tiles_match_cpu_oracle(workdir):
+    """Reads far longer than 160 tiles (the count matrix of the smoothing passes leaves shared
+    memory, the human-scale config's 200 kbp reads at tile 1000 do the same): log-normal lengths with
+    N50 20 kbp at tile length 100, i.e. 200 tiles typical and up to 2000, against the CPU oracle byte
+    for byte."""
+    import subprocess
+    sp = grb.api.synth_params(400000, 12.0, 0, 91, n50=20000)
+    data = grb.synth_fastq(sp)
+    fq = os.path.join(workdir, "longreads.fq")
+    with open(fq, "wb") as f:
+        f.write(data)
+    params = dict(kmer_size=22, weight=16, hash_num=3, tile_length=100, block_size=10,
+                  unassigned_min=5, assigned_max=1, occupancy=0.1, threshold=10, phred_delta=5,
+                  ratio=0.9, max_paths=3, min_length=2000, silver_path=1, phred_min=15,
+                  genome_size=400000)
+    res = grb.run_path(data, input_path=fq, prefix=os.path.join(workdir, "long.gpu"), quiet=True,
+                       seed_preset=SEED22, **params)
+    args = ["-k", "22", "-w", "16", "-s", SEED22, "-h", "3", "-t", "100", "-b", "10", "-u", "5", "-a",
+            "1", "-o", "0.1", "-x", "10", "-d", "5", "-r", "0.9", "-M", "3", "-m", "2000", "-P", "15",
+            "-g", "400000", "--silver_path"]
+    subprocess.check_call([pu.ORACLE] + args + ["-j", "8", "-i", fq, "-p",
+                                                os.path.join(workdir, "long.cpu")],
+                          stderr=subprocess.DEVNULL)
+    n_files = 0
+    for i in range(1, 4):
+        g, c = (os.path.join(workdir, f"long.{t}_{i}.fq") for t in ("gpu", "cpu"))
+        assert os.path.exists(g) == os.path.exists(c), i
+        if os.path.exists(c):
+            n_files += 1
+            with open(g, "rb") as fg, open(c, "rb") as fc:
+                assert pu.golden_cases.md5(fg.read()) == pu.golden_cases.md5(fc.read()), i
+    assert n_files >= 1 and res.reads_selected > 0
