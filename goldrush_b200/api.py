@@ -137,6 +137,8 @@ def lib():
         "grb_cached_memory_bytes": (u64, []),
         "grb_release_cached_memory": (None, []),
         "grb_reads_reserve": (i32, [vp, u64]),
+        "grb_host_pin": (i32, [vp, sz, P(sz)]),
+        "grb_host_unpin": (None, [vp, sz]),
         "grb_reads_ingest_fastq": (i32, [vp, vp, sz, i32, P(sz)]),
         "grb_reads_readahead": (i32, [vp, vp, sz]),
         "grb_reads_count": (u64, [vp]),

@@ -170,6 +170,53 @@ grb_arena_give(void* p)
   g_arena_idle.push_back(p);
 }
 
+// Host ranges page-locked by grb_host_pin, in pieces of kPinPiece bytes each registered on its own:
+// one cudaMemcpyAsync must not span two registrations (or a registered and an unregistered part),
+// so the ingest copies are cut at the piece boundaries.
+static const size_t kPinPiece = (size_t)1 << 30;
+struct GrbPin
+{
+  const char* base;
+  size_t bytes;
+};
+static std::mutex g_pin_mu;
+static std::vector<GrbPin> g_pins;
+
+static cudaError_t
+grb_copy_h2d(void* dst, const char* src, size_t n, cudaStream_t s)
+{
+  GrbPin pin{ nullptr, 0 };
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    for (const GrbPin& q : g_pins) {
+      if (src + n > q.base && src < q.base + q.bytes) {
+        pin = q;
+        break;
+      }
+    }
+  }
+  if (!pin.base) {
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s);
+  }
+  size_t done = 0;
+  while (done < n) {
+    const char* at = src + done;
+    size_t len = n - done;
+    if (at < pin.base) {
+      len = std::min<size_t>(len, (size_t)(pin.base - at));
+    } else if (at < pin.base + pin.bytes) {
+      const size_t in_piece = kPinPiece - (size_t)(at - pin.base) % kPinPiece;
+      len = std::min(len, std::min<size_t>(in_piece, (size_t)(pin.base + pin.bytes - at)));
+    }
+    const cudaError_t e = cudaMemcpyAsync((char*)dst + done, at, len, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+      return e;
+    }
+    done += len;
+  }
+  return cudaSuccess;
+}
+
 struct grb_ctx
 {
   grb_params p{};
@@ -890,6 +937,46 @@ grb_reads_clear(grb_ctx* c)
 }
 
 int
+grb_host_pin(void* p, size_t n, size_t* pinned_bytes)
+{
+  size_t done = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    while (done < n) {
+      const size_t len = std::min(kPinPiece, n - done);
+      if (cudaHostRegister((char*)p + done, len, cudaHostRegisterDefault) != cudaSuccess) {
+        cudaGetLastError(); // not an error of the caller's later CUDA calls
+        break;
+      }
+      done += len;
+    }
+    if (done) {
+      g_pins.push_back(GrbPin{ (const char*)p, done });
+    }
+  }
+  if (pinned_bytes) {
+    *pinned_bytes = done;
+  }
+  return GRB_OK;
+}
+
+void
+grb_host_unpin(void* p, size_t pinned_bytes)
+{
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  for (size_t done = 0; done < pinned_bytes; done += kPinPiece) {
+    cudaHostUnregister((char*)p + done);
+  }
+  cudaGetLastError();
+  for (size_t i = 0; i < g_pins.size(); ++i) {
+    if (g_pins[i].base == (const char*)p) {
+      g_pins.erase(g_pins.begin() + i);
+      break;
+    }
+  }
+}
+
+int
 grb_reads_reserve(grb_ctx* c, uint64_t fastq_bytes)
 {
   cudaSetDevice(c->device);
@@ -947,7 +1034,7 @@ grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_
     GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, c->d_raw2.p + c->pf_dev_off + (bytes - c->pf_host), n,
                                 cudaMemcpyDeviceToDevice, s));
   } else {
-    GRB_CUDA(c, cudaMemcpyAsync(c->d_raw.p, bytes, n, cudaMemcpyHostToDevice, s));
+    GRB_CUDA(c, grb_copy_h2d(c->d_raw.p, bytes, n, s));
   }
   c->pf_host = nullptr;
   if (c->ra_base && bytes >= c->ra_base && bytes + n < c->ra_base + c->ra_total) {
@@ -990,7 +1077,7 @@ grb_reads_ingest_fastq(grb_ctx* c, const char* bytes, size_t n, int final, size_
       k_copy_host<<<64, 256, 0, c->copy_stream>>>(c->d_raw2.p + c->pf_dev_off, dev_view, len);
       c->launches += 1;
     } else {
-      GRB_CUDA(c, cudaMemcpyAsync(c->d_raw2.p, lo, len, cudaMemcpyHostToDevice, c->copy_stream));
+      GRB_CUDA(c, grb_copy_h2d(c->d_raw2.p, lo, len, c->copy_stream));
     }
     GRB_CUDA(c, cudaEventRecord(c->ra_ready, c->copy_stream));
     c->pf_host = lo;

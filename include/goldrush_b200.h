@@ -86,6 +86,13 @@ uint64_t grb_launch_count(const grb_ctx* ctx);
  * calls report and empty that cache; GRB_POOL=0 in the environment disables it. */
 uint64_t grb_cached_memory_bytes(void);
 void grb_release_cached_memory(void);
+/* Page-locks a host range for the ingest copies (cudaHostRegister in pieces of 1 GiB, so that a
+ * range larger than the system lets one call lock is pinned as far as possible: the copies of the
+ * rest go through the driver's staging buffer, slower but correct).  *pinned_bytes = leading bytes
+ * that are now page-locked.  grb_host_unpin releases what grb_host_pin locked. */
+int grb_host_pin(void* p, size_t n, size_t* pinned_bytes);
+void grb_host_unpin(void* p, size_t pinned_bytes);
+
 /* Size hint before the first grb_reads_ingest_fastq: total FASTQ bytes to come, so that the read
  * store is allocated once instead of grown chunk by chunk. */
 int grb_reads_reserve(grb_ctx* ctx, uint64_t fastq_bytes);
