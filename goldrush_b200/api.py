@@ -146,6 +146,7 @@ def lib():
         "grb_reads_allgather": (i32, [vp]),
         "grb_reads_own_range": (i32, [vp, P(u64), P(u64)]),
         "grb_comm_allgather_host": (i32, [vp, vp, u64, vp, u64, P(u64)]),
+        "grb_comm_exchange_host": (i32, [vp, vp, u32, vp, u32]),
         "grb_reads_get_meta": (i32, [vp, u64, u64, P(ReadMeta)]),
         "grb_reads_set_flags": (i32, [vp, u64, u64, vp]),
         "grb_reads_clear": (None, [vp]),

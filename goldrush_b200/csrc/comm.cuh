@@ -30,6 +30,8 @@ struct GrbNccl
                             cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -51,7 +53,7 @@ grb_comm()
   return *g;
 }
 
-// binds the eight NCCL entry points; returns false and sets g.err if no libnccl can be found
+// binds the ten NCCL entry points; returns false and sets g.err if no libnccl can be found
 inline bool
 grb_nccl_load(GrbComm& g)
 {
@@ -76,10 +78,13 @@ grb_nccl_load(GrbComm& g)
   a.CommDestroy = (decltype(a.CommDestroy))dlsym(lib, "ncclCommDestroy");
   a.AllGather = (decltype(a.AllGather))dlsym(lib, "ncclAllGather");
   a.Broadcast = (decltype(a.Broadcast))dlsym(lib, "ncclBroadcast");
+  a.Send = (decltype(a.Send))dlsym(lib, "ncclSend");
+  a.Recv = (decltype(a.Recv))dlsym(lib, "ncclRecv");
   a.GroupStart = (decltype(a.GroupStart))dlsym(lib, "ncclGroupStart");
   a.GroupEnd = (decltype(a.GroupEnd))dlsym(lib, "ncclGroupEnd");
   a.GetErrorString = (decltype(a.GetErrorString))dlsym(lib, "ncclGetErrorString");
-  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.Broadcast ||
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.Broadcast || !a.Send ||
+      !a.Recv ||
       !a.GroupStart ||
       !a.GroupEnd || !a.GetErrorString) {
     g.err = "libnccl lacks one of the entry points this library binds";

@@ -1363,6 +1363,88 @@ grb_comm_allgather_host(grb_ctx* c, const void* send, uint64_t n, void* out, uin
 }
 
 int
+grb_comm_exchange_host(grb_ctx* c, const grb_host_msg* sends, uint32_t n_sends, const grb_host_msg* recvs,
+                       uint32_t n_recvs)
+{
+  cudaSetDevice(c->device);
+  const int me = c->comm ? c->comm->rank : 0;
+  // messages to oneself: matched in list order, copied on the host
+  {
+    uint32_t ri = 0;
+    for (uint32_t i = 0; i < n_sends; ++i) {
+      if (sends[i].peer != me) {
+        continue;
+      }
+      while (ri < n_recvs && recvs[ri].peer != me) {
+        ++ri;
+      }
+      if (ri == n_recvs || recvs[ri].bytes != sends[i].bytes) {
+        return c->fail(GRB_ERR_ARG, "grb_comm_exchange_host: unmatched message to self");
+      }
+      memcpy(recvs[ri].ptr, sends[i].ptr, sends[i].bytes);
+      ++ri;
+    }
+  }
+  if (!c->comm) {
+    return GRB_OK;
+  }
+  GrbComm& g = *c->comm;
+  cudaStream_t s = c->stream;
+  uint64_t out_bytes = 0, in_bytes = 0;
+  for (uint32_t i = 0; i < n_sends; ++i) {
+    out_bytes += sends[i].peer != me ? (sends[i].bytes + 15) / 16 * 16 : 0;
+  }
+  for (uint32_t i = 0; i < n_recvs; ++i) {
+    in_bytes += recvs[i].peer != me ? (recvs[i].bytes + 15) / 16 * 16 : 0;
+  }
+  DevBuf<uint8_t> d_out, d_in;
+  GRB_CUDA(c, d_out.reserve_exact(std::max<uint64_t>(out_bytes, 16), s));
+  GRB_CUDA(c, d_in.reserve_exact(std::max<uint64_t>(in_bytes, 16), s));
+  uint64_t at = 0;
+  for (uint32_t i = 0; i < n_sends; ++i) {
+    if (sends[i].peer != me && sends[i].bytes) {
+      GRB_CUDA(c, cudaMemcpyAsync(d_out.p + at, sends[i].ptr, sends[i].bytes, cudaMemcpyHostToDevice, s));
+    }
+    at += sends[i].peer != me ? (sends[i].bytes + 15) / 16 * 16 : 0;
+  }
+  ncclResult_t r = g.api.GroupStart();
+  at = 0;
+  for (uint32_t i = 0; i < n_sends && r == ncclSuccess; ++i) {
+    if (sends[i].peer != me) {
+      if (sends[i].bytes) {
+        r = g.api.Send(d_out.p + at, sends[i].bytes, ncclUint8, sends[i].peer, g.comm, s);
+      }
+      at += (sends[i].bytes + 15) / 16 * 16;
+    }
+  }
+  at = 0;
+  for (uint32_t i = 0; i < n_recvs && r == ncclSuccess; ++i) {
+    if (recvs[i].peer != me) {
+      if (recvs[i].bytes) {
+        r = g.api.Recv(d_in.p + at, recvs[i].bytes, ncclUint8, recvs[i].peer, g.comm, s);
+      }
+      at += (recvs[i].bytes + 15) / 16 * 16;
+    }
+  }
+  const ncclResult_t r2 = g.api.GroupEnd();
+  if (r != ncclSuccess || r2 != ncclSuccess) {
+    return c->fail_nccl(r != ncclSuccess ? r : r2, "ncclSend / ncclRecv (host messages)");
+  }
+  at = 0;
+  for (uint32_t i = 0; i < n_recvs; ++i) {
+    if (recvs[i].peer != me) {
+      if (recvs[i].bytes) {
+        GRB_CUDA(c, cudaMemcpyAsync(recvs[i].ptr, d_in.p + at, recvs[i].bytes, cudaMemcpyDeviceToHost, s));
+      }
+      at += (recvs[i].bytes + 15) / 16 * 16;
+    }
+  }
+  GRB_CUDA(c, cudaStreamSynchronize(s));
+  c->launches += 1;
+  return GRB_OK;
+}
+
+int
 grb_reads_get_meta(grb_ctx* c, uint64_t first, uint64_t count, grb_read_meta* out)
 {
   if (first + count > c->n_reads) {

@@ -19,6 +19,7 @@
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <future>
+#include <memory>
 #include <thread>
 #include <unistd.h>
 #include <unordered_set>
@@ -52,6 +53,28 @@ struct Fnv
     }
   }
 };
+
+// Hash of one output record (grb_run_result.out_digest folds these in output order): FNV-1a over
+// the record's bytes taken as little-endian 8-byte words (the last word zero-padded), then the
+// length.  One multiply per 8 bytes: the byte-wise form hashed under 1 GB/s per thread, which made
+// the record assembly -- not the GPU -- the slowest stage of a human-scale run on 4 cores per rank.
+uint64_t
+record_hash(const char* p, size_t n)
+{
+  uint64_t h = 1469598103934665603ull;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    h = (h ^ w) * 1099511628211ull;
+  }
+  if (i < n) {
+    uint64_t w = 0;
+    memcpy(&w, p + i, n - i);
+    h = (h ^ w) * 1099511628211ull;
+  }
+  return (h ^ (uint64_t)n) * 1099511628211ull;
+}
 
 struct OutFile
 {
@@ -163,11 +186,22 @@ log_path_stat(const Log& log, uint64_t curr_path, const grb_path_stats& s, doubl
 
 } // namespace
 
-// `capture` (may be NULL) receives the bytes of every output record, one buffer per output file
-// (capture[n - 1] = what <p>_n.fq holds), for grb_run_two_stage.
+// What grb_run_two_stage takes over from the silver stage: the bytes of every output record, one
+// buffer per output file (per_path[n - 1] = what <p>_n.fq holds; slice mode: this rank's records
+// only), and at the end of the stage `joined`: what `cat <p>_*.fq` gives, on every rank.
+struct Capture
+{
+  std::vector<std::vector<char>> per_path;
+  std::unique_ptr<char[]> joined;
+  size_t joined_len = 0;
+  // several ranks in slice mode: `joined` is this rank's consecutive share of the joined paths
+  // (bytes [slice_offset, slice_offset + joined_len) of slice_total), cut between records
+  uint64_t slice_offset = 0, slice_total = 0;
+};
+
 static int
 run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_run_result* res,
-              char* err, size_t err_cap, std::vector<std::vector<char>>* capture)
+              char* err, size_t err_cap, Capture* cap_out)
 {
   const double t_wall0 = now_ms();
   const bool timing = getenv("GRB_TIMING") != nullptr; // host-side phase clock on stderr
@@ -180,6 +214,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     }
   };
   grb_run_result R{};
+  std::vector<std::vector<char>>* capture = cap_out ? &cap_out->per_path : nullptr;
   const Log log{ !o->quiet };
   grb_params p = o->params;
 
@@ -425,6 +460,10 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     }
   }
   n_threads = std::min(n_threads, 64);
+  // record assembly runs beside pass 2: with several ranks sharing the host, the thread that
+  // launches the kernels and NCCL's proxy thread must keep a core each, or every collective of the
+  // lock-stepped ranks waits for whichever rank was descheduled last
+  const int emit_threads = c_world_now > 1 ? std::max(1, n_threads - 2) : n_threads;
 
   // ---- per-read Phred statistics from the device sums ----
   std::vector<uint32_t> avg(nreads), delta(nreads);
@@ -666,7 +705,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   {
     uint64_t read;
     size_t s0, sl, ql;
-    size_t at, bytes;   // position inside the chunk buffer
+    size_t at, bytes;   // position inside the chunk buffer (or inside the capture buffer of its path)
     uint32_t id_len;
     bool trimmed, closes_path;
     double phred;
@@ -764,10 +803,36 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
         bytes += recs[r1].bytes;
         ++r1;
       }
-      if (want_bytes && buf.size() < bytes) {
+      if (capture) {
+        // two-stage call: the records are assembled straight into the buffer of their path (no copy
+        // afterwards); the buffers grow once per chunk of records
+        std::vector<size_t> grow;
+        for (size_t ri = r0; ri < r1; ++ri) {
+          const uint32_t pth = dec[recs[ri].read].path;
+          if (capture->size() < pth) {
+            capture->resize(pth);
+          }
+          if (grow.size() < pth) {
+            grow.resize(pth, 0);
+          }
+          recs[ri].at = (*capture)[pth - 1].size() + grow[pth - 1];
+          grow[pth - 1] += recs[ri].bytes;
+        }
+        for (size_t q = 0; q < grow.size(); ++q) {
+          std::vector<char>& cp = (*capture)[q];
+          if (grow[q]) {
+            if (cp.capacity() < cp.size() + grow[q]) { // a path ends near ratio * genome bases: about 2.1 bytes each
+              cp.reserve(std::max<size_t>(cp.size() + grow[q],
+                                          std::max<size_t>(2 * cp.capacity(), (size_t)(2.1 * p.ratio * p.genome_size) /
+                                                                                (size_t)std::max(1, slice_mode ? c_world_now : 1))));
+            }
+            cp.resize(cp.size() + grow[q]);
+          }
+        }
+      } else if (want_bytes && buf.size() < bytes) {
         buf.resize(bytes);
       }
-#pragma omp parallel num_threads(n_threads)
+#pragma omp parallel num_threads(emit_threads)
       {
         std::vector<char> local; // record scratch when nothing is written (digest only)
 #pragma omp for schedule(dynamic, 4)
@@ -775,7 +840,9 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
           Rec& r = recs[ri];
           const grb_read_meta& m = meta[r.read];
           char* dst;
-          if (want_bytes) {
+          if (capture) {
+            dst = (*capture)[dec[r.read].path - 1].data() + r.at;
+          } else if (want_bytes) {
             dst = buf.data() + r.at;
           } else {
             if (local.size() < r.bytes) {
@@ -795,6 +862,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
             w += 11;
           }
           const char* sq = data + (m.seq_off - data_origin) + r.s0;
+#pragma omp simd
           for (size_t j = 0; j < r.sl; ++j) { // SeqReader folds the sequence to upper case
             const unsigned char ch = (unsigned char)sq[j];
             w[j] = (char)(ch - (((unsigned)(ch - 'a') < 26u) << 5));
@@ -809,9 +877,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
             w += r.ql;
             *w++ = '\n';
           }
-          Fnv hsh;
-          hsh.add(dst, r.bytes);
-          r.hash = hsh.h;
+          r.hash = record_hash(dst, r.bytes);
           // the reference adds sum_phred of the written quality string (goldrush_path.cpp:1005-1008);
           // for a whole read that is the running sum the device already holds
           r.phred = 0;
@@ -824,29 +890,15 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
         const Rec& r = recs[ri];
         if (slice_mode) {
           own_pairs.push_back(HashPhred{ r.hash, r.phred });
-          if (capture) {
-            const uint32_t pth = dec[r.read].path;
-            if (capture->size() < pth) {
-              capture->resize(pth);
-            }
-            std::vector<char>& cp = (*capture)[pth - 1];
-            cp.insert(cp.end(), buf.data() + r.at, buf.data() + r.at + r.bytes);
-          }
           continue;
         }
         if (out.f) {
-          fwrite(buf.data() + r.at, 1, r.bytes, out.f);
+          const char* src = capture ? (*capture)[dec[r.read].path - 1].data() + r.at : buf.data() + r.at;
+          fwrite(src, 1, r.bytes, out.f);
         }
         digest.add((const char*)&r.hash, 8);
         phred_sum += r.phred;
         path_now = dec[r.read].path;
-        if (capture) {
-          if (capture->size() < path_now) {
-            capture->resize(path_now);
-          }
-          std::vector<char>& cp = (*capture)[path_now - 1];
-          cp.insert(cp.end(), buf.data() + r.at, buf.data() + r.at + r.bytes);
-        }
         if (r.closes_path) {
           if (o->verbose) {
             log_path_stat(log, path_now, snaps[snap_i], phred_sum);
@@ -862,7 +914,10 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     }
   };
 
-  uint64_t slice = 16384;
+  // reads per grb_select_reads call: long enough that the calls' fixed costs (a handful of host
+  // round trips each) stay small on inputs of millions of reads, short enough that the record
+  // assembly of one slice has the next slice's device time to hide under
+  uint64_t slice = std::min<uint64_t>(262144, std::max<uint64_t>(16384, nreads / 64));
   if (const char* e = getenv("GRB_SLICE_READS")) { // 0 = one call for the whole store
     const long long v = atoll(e);
     slice = v <= 0 ? nreads : (uint64_t)v;
@@ -950,30 +1005,137 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     }
     log("assigned\nin %.4f\n", R.ms_pass2 / 1e3);
   }
-  if (capture && slice_mode && c_world_now > 1) {
-    // two-stage call in slice mode: every rank holds the records of its own reads only; each path
-    // is put together from the ranks' parts (rank order = read order) on every rank
-    const uint32_t n_paths = (uint32_t)std::min<uint64_t>(curr_path, std::max<uint64_t>(1, p.max_paths));
+  if (cap_out) {
+    // The golden run's input: `cat $(p1)_*.fq` (bin/goldrush:250-251).  The shell expands the glob in
+    // lexicographic order of the file names (_1, _10, _11, _2, ...), and the selection depends on
+    // read order, so the paths are joined in that order, not numerically.  Slice mode: every rank
+    // holds the records of its own reads only, and each path is put together from the ranks' parts
+    // (rank order = read order) on every rank, straight into its place in the joined buffer.
+    const bool spread = slice_mode && c_world_now > 1;
+    const uint32_t n_paths =
+      spread ? (uint32_t)std::min<uint64_t>(curr_path, std::max<uint64_t>(1, p.max_paths))
+             : (uint32_t)capture->size();
     capture->resize(n_paths);
-    std::vector<uint64_t> sizes((size_t)c_world_now);
-    for (uint32_t q = 0; q < n_paths; ++q) {
-      std::vector<char>& part = (*capture)[q];
-      uint64_t mine = part.size(), total = 0;
-      std::vector<uint64_t> all_sizes((size_t)c_world_now);
-      if ((rc = grb_comm_allgather_host(ctx, &mine, 8, all_sizes.data(), all_sizes.size() * 8,
-                                        sizes.data())) != GRB_OK) {
-        return fail(rc);
-      }
-      for (uint64_t v : all_sizes) {
-        total += v;
-      }
-      std::vector<char> whole(total);
-      if ((rc = grb_comm_allgather_host(ctx, part.data(), part.size(), whole.data(), whole.size(),
-                                        sizes.data())) != GRB_OK) {
-        return fail(rc);
-      }
-      part.swap(whole);
+    std::vector<size_t> order(n_paths);
+    for (size_t i = 0; i < order.size(); ++i) {
+      order[i] = i;
     }
+    std::sort(order.begin(), order.end(), [](size_t a, size_t b) {
+      return std::to_string(a + 1) + ".fq" < std::to_string(b + 1) + ".fq";
+    });
+    std::vector<uint64_t> mine(n_paths), all((size_t)n_paths * c_world_now), sizes((size_t)c_world_now);
+    for (uint32_t q = 0; q < n_paths; ++q) {
+      mine[q] = (*capture)[q].size();
+    }
+    if (spread) {
+      if ((rc = grb_comm_allgather_host(ctx, mine.data(), mine.size() * 8, all.data(), all.size() * 8,
+                                        sizes.data())) != GRB_OK) {
+        return fail(rc);
+      }
+    } else {
+      all = mine;
+    }
+    const int ranks = spread ? c_world_now : 1;
+    size_t total = 0;
+    for (uint64_t v : all) {
+      total += v;
+    }
+    // Slice mode: the joined stream is a sequence of parts (path q, rank r), q in glob order, r in
+    // rank order; the golden stage gives rank g a run of whole parts of about total / W bytes (the
+    // ranks' shares of a path are about equal: reads are in random order), sent point to point
+    // over NVLink.  No rank ever holds the whole silver output.
+    bool redistributed = false;
+    if (spread && total > 0) {
+      struct Part
+      {
+        size_t q;
+        int r;
+        uint64_t start, bytes;
+        int to;
+      };
+      std::vector<Part> parts;
+      uint64_t cum = 0;
+      for (size_t q : order) {
+        for (int r = 0; r < ranks; ++r) {
+          const uint64_t b = all[(size_t)r * n_paths + q];
+          parts.push_back(Part{ q, r, cum, b, 0 });
+          cum += b;
+        }
+      }
+      std::vector<uint64_t> got((size_t)ranks, 0);
+      int prev = 0;
+      for (Part& pt : parts) {
+        int to = (int)std::min<uint64_t>((uint64_t)ranks - 1,
+                                         (uint64_t)((unsigned __int128)(pt.start + pt.bytes / 2) * (unsigned)ranks / total));
+        to = std::max(to, prev);
+        prev = to;
+        pt.to = to;
+        got[(size_t)to] += pt.bytes;
+      }
+      bool all_fed = true;
+      for (uint64_t v : got) {
+        all_fed = all_fed && v > 0;
+      }
+      if (all_fed) {
+        int me = 0, w = 1;
+        grb_comm_info(ctx, &me, &w);
+        cap_out->joined.reset(new char[std::max<uint64_t>(got[(size_t)me], 1)]);
+        cap_out->joined_len = got[(size_t)me];
+        cap_out->slice_total = total;
+        std::vector<grb_host_msg> sends, recvs;
+        uint64_t at_local = 0;
+        bool first = true;
+        for (const Part& pt : parts) {
+          if (pt.r == me && pt.bytes) {
+            sends.push_back(grb_host_msg{ pt.to, 0, (*capture)[pt.q].data(), pt.bytes });
+          }
+          if (pt.to == me) {
+            if (first) {
+              cap_out->slice_offset = pt.start;
+              first = false;
+            }
+            if (pt.bytes) {
+              recvs.push_back(grb_host_msg{ pt.r, 0, cap_out->joined.get() + at_local, pt.bytes });
+            }
+            at_local += pt.bytes;
+          }
+        }
+        if ((rc = grb_comm_exchange_host(ctx, sends.data(), (uint32_t)sends.size(), recvs.data(),
+                                         (uint32_t)recvs.size())) != GRB_OK) {
+          return fail(rc);
+        }
+        for (auto& v : *capture) {
+          std::vector<char>().swap(v);
+        }
+        redistributed = true;
+      }
+    }
+    if (!redistributed) {
+      cap_out->joined.reset(new char[std::max<size_t>(total, 1)]);
+      cap_out->joined_len = total;
+    }
+    size_t at = 0;
+    for (size_t q : order) {
+      if (redistributed) {
+        break;
+      }
+      size_t path_bytes = 0;
+      for (int r = 0; r < ranks; ++r) {
+        path_bytes += all[(size_t)r * n_paths + q];
+      }
+      std::vector<char>& part = (*capture)[q];
+      if (spread) {
+        if ((rc = grb_comm_allgather_host(ctx, part.data(), part.size(), cap_out->joined.get() + at,
+                                          path_bytes, sizes.data())) != GRB_OK) {
+          return fail(rc);
+        }
+      } else if (path_bytes) {
+        memcpy(cap_out->joined.get() + at, part.data(), path_bytes);
+      }
+      std::vector<char>().swap(part);
+      at += path_bytes;
+    }
+    mark("join paths");
   }
   R.launches = grb_launch_count(ctx);
   R.out_digest = digest.h;
@@ -1004,33 +1166,19 @@ grb_run_two_stage(const grb_run_options* silver, const grb_run_options* golden, 
     return set_err(err, err_cap, "grb_run_two_stage: first stage must be --silver_path, second not",
                    GRB_ERR_ARG);
   }
-  std::vector<std::vector<char>> per_path;
-  int rc = run_path_impl(silver, fastq, fastq_len, res_silver, err, err_cap, &per_path);
+  Capture cap;
+  int rc = run_path_impl(silver, fastq, fastq_len, res_silver, err, err_cap, &cap);
   if (rc != GRB_OK) {
     return rc;
   }
-  // bin/goldrush:250-251 builds the golden run's input with `cat $(p1)_*.fq`: the shell expands the
-  // glob in lexicographic order of the file names (_1, _10, _11, _2, ...), and the selection depends
-  // on read order, so the paths are joined in that order, not numerically
-  std::vector<size_t> order(per_path.size());
-  for (size_t i = 0; i < order.size(); ++i) {
-    order[i] = i;
-  }
-  std::sort(order.begin(), order.end(), [](size_t a, size_t b) {
-    return std::to_string(a + 1) + ".fq" < std::to_string(b + 1) + ".fq";
-  });
-  std::vector<char> paths;
-  for (size_t i : order) {
-    paths.insert(paths.end(), per_path[i].begin(), per_path[i].end());
-    std::vector<char>().swap(per_path[i]);
-  }
-  if (paths.empty()) { // the golden run would stop on an empty file (goldrush_path.cpp:247-250)
+  if (cap.joined_len == 0) { // the golden run would stop on an empty file (goldrush_path.cpp:247-250)
     return set_err(err, err_cap, "grb_run_two_stage: the silver stage selected no read", GRB_ERR_FORMAT);
   }
   grb_run_options g = *golden;
-  g.fastq_offset = g.fastq_total = 0; // the joined silver paths are whole on every rank
+  g.fastq_offset = cap.slice_offset; // slice mode: each rank holds its share of the joined paths
+  g.fastq_total = cap.slice_total;   // (0: the joined silver paths are whole on every rank)
   if (!g.input_path) {
     g.input_path = "(silver paths in memory)";
   }
-  return run_path_impl(&g, paths.data(), paths.size(), res_golden, err, err_cap, nullptr);
+  return run_path_impl(&g, cap.joined.get(), cap.joined_len, res_golden, err, err_cap, nullptr);
 }

@@ -266,6 +266,19 @@ int grb_query_sharded(const grb_ctx* ctx);
  * without communicator copies send to out.  Collective. */
 int grb_comm_allgather_host(grb_ctx* ctx, const void* send, uint64_t n, void* out, uint64_t out_cap,
                             uint64_t* sizes);
+/* Host-side point-to-point exchange through the communicator (staged through device memory, NCCL
+ * send / recv in one group): message i of `sends` goes to rank peer[i]; `recvs` lists what arrives,
+ * with the sizes the senders use.  Messages between one pair of ranks are matched in list order.
+ * A message to oneself is a host copy.  Collective: every rank calls it (possibly with empty lists). */
+typedef struct grb_host_msg
+{
+  int32_t peer;
+  int32_t pad;
+  void* ptr;
+  uint64_t bytes;
+} grb_host_msg;
+int grb_comm_exchange_host(grb_ctx* ctx, const grb_host_msg* sends, uint32_t n_sends,
+                           const grb_host_msg* recvs, uint32_t n_recvs);
 
 /* ---- plumbing for callers that issue their own collectives (e.g. torch.distributed) on the raw
  * device pointers ---- */
@@ -372,7 +385,11 @@ typedef struct grb_run_result
   double ms_pass2;
   double ms_wall;             /* host wall clock of the whole call */
   uint64_t launches;
-  uint64_t out_digest;        /* FNV-1a over the per-record FNV-1a hashes of the output records, in output order (also when nothing is written) */
+  uint64_t out_digest;        /* order-sensitive digest of the output records (also when nothing is
+                                 written): FNV-1a over the 8-byte hashes of the records in output
+                                 order, a record's hash being FNV-1a over its bytes taken as
+                                 little-endian 8-byte words (last word zero-padded), then its length.
+                                 oracle/grb_digest.cpp computes the same from output files. */
 } grb_run_result;
 
 int grb_run_path(const grb_run_options* opt, const char* fastq, size_t fastq_len,

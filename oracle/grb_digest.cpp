@@ -1,6 +1,8 @@
 // TEST INFRASTRUCTURE ONLY.  grb-digest: the order-sensitive digest of a goldrush-path output, as
 // grb_run_result.out_digest defines it (include/goldrush_b200.h): FNV-1a over the 8-byte FNV-1a
-// hashes of the output records, in output order.  A record is 4 lines of a silver-path FASTQ
+// hashes of the output records, in output order; a record's hash is FNV-1a over its bytes taken as
+// little-endian 8-byte words (last word zero-padded), then its length.  A record is 4 lines of a
+// silver-path FASTQ
 // (goldrush_path.cpp:996-1002) or 2 lines of the golden-path FASTA (:1063-1070).
 //   grb-digest <p>_1.fq <p>_2.fq ...      (files in path order)   |   grb-digest <p>.fa
 // prints: <digest as decimal> <records> <bytes>
@@ -33,8 +35,7 @@ main(int argc, char** argv)
     }
     const size_t nl = strlen(argv[a]);
     const int lines_per_record = (nl > 3 && strcmp(argv[a] + nl - 3, ".fa") == 0) ? 2 : 4;
-    std::vector<unsigned char> buf((size_t)64 << 20);
-    uint64_t h = kInit;
+    std::vector<unsigned char> buf((size_t)64 << 20), rec;
     int lines = 0;
     size_t got;
     while ((got = fread(buf.data(), 1, buf.size(), f)) > 0) {
@@ -43,12 +44,25 @@ main(int argc, char** argv)
       while (i < got) {
         const unsigned char* nlp = (const unsigned char*)memchr(buf.data() + i, '\n', got - i);
         const size_t end = nlp ? (size_t)(nlp - buf.data()) + 1 : got;
-        h = fnv(h, buf.data() + i, end - i);
+        rec.insert(rec.end(), buf.data() + i, buf.data() + end);
         i = end;
         if (nlp && ++lines == lines_per_record) {
+          uint64_t h = kInit;
+          size_t q = 0;
+          for (; q + 8 <= rec.size(); q += 8) {
+            uint64_t w;
+            memcpy(&w, rec.data() + q, 8);
+            h = (h ^ w) * 1099511628211ull;
+          }
+          if (q < rec.size()) {
+            uint64_t w = 0;
+            memcpy(&w, rec.data() + q, rec.size() - q);
+            h = (h ^ w) * 1099511628211ull;
+          }
+          h = (h ^ (uint64_t)rec.size()) * 1099511628211ull;
           digest = fnv(digest, (const unsigned char*)&h, 8);
           ++records;
-          h = kInit;
+          rec.clear();
           lines = 0;
         }
       }
