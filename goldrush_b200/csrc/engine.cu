@@ -308,9 +308,13 @@ struct grb_ctx
   DevBuf<uint32_t> bb_uq, bb_nu, bb_cm, bb_sp_nas;
   DevBuf<GrbReadPlan> bb_sp_plan;
   DevBuf<uint32_t> bb_sp_adv, bb_rd_hits, bb_rd_miss, bb_rd_q;
-  DevBuf<uint64_t> bb_read_idx, bb_cm_off; // chunk descriptors
-  DevBuf<uint32_t> bb_tile_first, bb_tile_read;
-  DevBuf<uint64_t> bb_dec_idx;
+  // chunk descriptors, two sets: chunk k + 1 is described and queued while chunk k still runs
+  DevBuf<uint64_t> bb_read_idx[2], bb_cm_off[2];
+  DevBuf<uint32_t> bb_tile_first[2], bb_tile_read[2];
+  DevBuf<uint64_t> bb_dec_idx[2];
+  int bb_set = 0;                 // the set the batches being launched read
+  GrbSelState* h_state = nullptr; // pinned: loop state as of the end of each of the two chunks in flight
+  cudaEvent_t ev_chunk[2] = { nullptr, nullptr };
   // per-batch query outputs and the probe index of the commit
   uint64_t b2_cap_tiles = 0, b2_ix_entries = 0;
   uint32_t b2_cap_reads = 0;
@@ -734,6 +738,11 @@ grb_destroy(grb_ctx* c)
   }
   if (c->up_host) {
     grb_arena_give(c->up_host);
+  }
+  if (c->h_state) {
+    cudaFreeHost(c->h_state);
+    cudaEventDestroy(c->ev_chunk[0]);
+    cudaEventDestroy(c->ev_chunk[1]);
   }
   if (c->b3_dbg.p && getenv("GRB_FIX_DEBUG")) {
     std::vector<uint32_t> h(c->b3_dbg.cap);
@@ -2501,9 +2510,9 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   cudaStream_t s = c->stream;
   const uint64_t T = c->tile_frames, h = c->h_seed.h; // T: frames per tile
   GrbBatchDev bd{};
-  bd.read_idx = c->bb_read_idx.p + b.read0;
-  bd.tile_first = c->bb_tile_first.p + b.tf0;
-  bd.tile_read = c->bb_tile_read.p + b.tr0;
+  bd.read_idx = c->bb_read_idx[c->bb_set].p + b.read0;
+  bd.tile_first = c->bb_tile_first[c->bb_set].p + b.tf0;
+  bd.tile_read = c->bb_tile_read[c->bb_set].p + b.tr0;
   bd.nb = b.nb;
   bd.n_bt = b.n_bt;
   bd.stash = c->bb_stash.p;
@@ -2514,7 +2523,7 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
   bd.uq = c->bb_uq.p;
   bd.nu = c->bb_nu.p;
   bd.cm = c->bb_cm.p;
-  bd.cm_off = c->bb_cm_off.p + b.read0;
+  bd.cm_off = c->bb_cm_off[c->bb_set].p + b.read0;
   bd.sp_n_as = c->bb_sp_nas.p;
   bd.sp_plan = c->bb_sp_plan.p;
   bd.sp_adv = c->bb_sp_adv.p;
@@ -2670,7 +2679,7 @@ launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
     GrbReadsDev reads = c->reads_dev();
     GrbSelState* st = c->d_state;
     grb_decision* dec = d_dec;
-    const uint64_t* dec_idx = c->bb_dec_idx.p + b.read0;
+    const uint64_t* dec_idx = c->bb_dec_idx[c->bb_set].p + b.read0;
     uint32_t us_a = us, n_cap_a = n_cap, dc_a = dc, cm_a = cm_smem;
     void* args[] = { &reads, &c->prm, &bd, &b3, &st, &dec, &dec_idx, &us_a, &n_cap_a, &dc_a, &cm_a };
     c->kbegin();
@@ -2737,19 +2746,29 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
     const uint64_t fit = c->p.genome_size / (2 * max_len);
     batch_reads = (uint32_t)std::min<uint64_t>(batch_reads, std::max<uint64_t>(32, fit));
   }
-  // batches queued between two looks at the loop state (path rollover / exit): after a rollover
-  // the rest of the chunk's launches return at once (state->halt) and the chunk is re-planned from
-  // the read after it, so a longer chunk trades a few empty launches per rollover (five per run)
-  // for fewer host round trips (35 -> 9 per cfg2 run)
+  // batches per chunk = between two looks at the loop state (path rollover / exit).  Chunks are
+  // pipelined two deep (below), so the device does not wait for the host between them; after a
+  // rollover the launches already queued return at once (state->halt) and the loop resumes at the
+  // read after it: a shorter chunk wastes fewer such launches (five rollovers per silver run)
   static const uint64_t chunk_batches = [] {
     const char* e = getenv("GRB_CHUNK_BATCHES");
     const long v = e ? strtol(e, nullptr, 10) : 0;
-    return (uint64_t)(v > 0 && v <= 1024 ? v : 8);
+    return (uint64_t)(v > 0 && v <= 1024 ? v : 4);
   }();
   const uint64_t kChunk = c->batch_mode ? chunk_batches * batch_reads : 256;
-  while (i < end && !c->sel_finished) {
-    uint64_t launched = 0, j = i;
-    if (c->batch_mode) {
+  if (c->batch_mode) {
+    // Chunks of batches are pipelined two deep: chunk k + 1 is planned, described and queued while
+    // chunk k runs, and only then is chunk k's loop state looked at (path rollover / exit).  A rollover
+    // inside chunk k makes every launch queued after it return at once (state->halt), and the loop
+    // resumes at the read after it -- the device never waits for the host between chunks.
+    if (!c->h_state) {
+      GRB_CUDA(c, cudaHostAlloc((void**)&c->h_state, 2 * sizeof(GrbSelState), cudaHostAllocDefault));
+      GRB_CUDA(c, cudaEventCreateWithFlags(&c->ev_chunk[0], cudaEventDisableTiming));
+      GRB_CUDA(c, cudaEventCreateWithFlags(&c->ev_chunk[1], cudaEventDisableTiming));
+    }
+    auto launch_chunk = [&](uint64_t from, int set, uint64_t* next) -> int {
+      uint64_t launched = 0, j = from;
+      c->bb_set = set;
       // cut the next kChunk visited reads into batches and describe them to the device
       BatchPlan bp;
       const uint64_t T = c->p.tile_length;
@@ -2795,21 +2814,21 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
         if (rc != GRB_OK) {
           return rc;
         }
-        GRB_CUDA(c, c->bb_read_idx.reserve(bp.read_idx.size(), 0, s));
-        GRB_CUDA(c, c->bb_tile_first.reserve(bp.tile_first.size(), 0, s));
-        GRB_CUDA(c, c->bb_tile_read.reserve(std::max<size_t>(1, bp.tile_read.size()), 0, s));
-        GRB_CUDA(c, cudaMemcpyAsync(c->bb_read_idx.p, bp.read_idx.data(), bp.read_idx.size() * 8,
+        GRB_CUDA(c, c->bb_read_idx[set].reserve(bp.read_idx.size(), 0, s));
+        GRB_CUDA(c, c->bb_tile_first[set].reserve(bp.tile_first.size(), 0, s));
+        GRB_CUDA(c, c->bb_tile_read[set].reserve(std::max<size_t>(1, bp.tile_read.size()), 0, s));
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_read_idx[set].p, bp.read_idx.data(), bp.read_idx.size() * 8,
                                     cudaMemcpyHostToDevice, s));
-        GRB_CUDA(c, c->bb_dec_idx.reserve(bp.dec_idx.size(), 0, s));
-        GRB_CUDA(c, cudaMemcpyAsync(c->bb_dec_idx.p, bp.dec_idx.data(), bp.dec_idx.size() * 8,
+        GRB_CUDA(c, c->bb_dec_idx[set].reserve(bp.dec_idx.size(), 0, s));
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_dec_idx[set].p, bp.dec_idx.data(), bp.dec_idx.size() * 8,
                                     cudaMemcpyHostToDevice, s));
-        GRB_CUDA(c, c->bb_cm_off.reserve(bp.cm_off.size(), 0, s));
-        GRB_CUDA(c, cudaMemcpyAsync(c->bb_cm_off.p, bp.cm_off.data(), bp.cm_off.size() * 8,
+        GRB_CUDA(c, c->bb_cm_off[set].reserve(bp.cm_off.size(), 0, s));
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_cm_off[set].p, bp.cm_off.data(), bp.cm_off.size() * 8,
                                     cudaMemcpyHostToDevice, s));
-        GRB_CUDA(c, cudaMemcpyAsync(c->bb_tile_first.p, bp.tile_first.data(),
+        GRB_CUDA(c, cudaMemcpyAsync(c->bb_tile_first[set].p, bp.tile_first.data(),
                                     bp.tile_first.size() * 4, cudaMemcpyHostToDevice, s));
         if (!bp.tile_read.empty()) {
-          GRB_CUDA(c, cudaMemcpyAsync(c->bb_tile_read.p, bp.tile_read.data(),
+          GRB_CUDA(c, cudaMemcpyAsync(c->bb_tile_read[set].p, bp.tile_read.data(),
                                       bp.tile_read.size() * 4, cudaMemcpyHostToDevice, s));
         }
         for (const BatchPlan::Batch& b : bp.batches) {
@@ -2819,51 +2838,100 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
           }
         }
       }
-    } else {
+      GRB_CUDA(c, cudaMemcpyAsync(&c->h_state[set], c->d_state, sizeof(GrbSelState), cudaMemcpyDeviceToHost, s));
+      GRB_CUDA(c, cudaEventRecord(c->ev_chunk[set], s));
+      *next = j;
+      return GRB_OK;
+    };
+    struct Queued
+    {
+      bool valid;
+      uint64_t next_i;
+      int set;
+    };
+    Queued prev{ false, 0, 0 };
+    int set = 0;
+    while (true) {
+      Queued cur{ false, 0, set };
+      if (i < end && !c->sel_finished) {
+        uint64_t j = i;
+        rc = launch_chunk(i, set, &j);
+        if (rc != GRB_OK) {
+          return rc;
+        }
+        cur = Queued{ true, j, set };
+      }
+      if (prev.valid) {
+        GRB_CUDA(c, cudaEventSynchronize(c->ev_chunk[prev.set]));
+        GrbSelState st = c->h_state[prev.set];
+        if (st.halt) {
+          if (cur.valid) { // queued behind the halt: nothing of it ran
+            GRB_CUDA(c, cudaEventSynchronize(c->ev_chunk[cur.set]));
+          }
+          if (st.n_snap && stats && n_stats && *n_stats < stats_cap) {
+            stats[(*n_stats)++] = st.snap;
+          }
+          if (st.finished) {
+            c->sel_finished = true;
+            stop_at = st.halt_read + 1;
+            break;
+          }
+          // rollover: reset_counts + reset_ID_vector, then resume after the read that triggered it
+          GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, (c->filt.pop + 1) * sizeof(GrbSlot), s));
+          st.halt = 0;
+          st.n_snap = 0;
+          GRB_CUDA(c, cudaMemcpyAsync(c->d_state, &st, sizeof st, cudaMemcpyHostToDevice, s));
+          GRB_CUDA(c, cudaStreamSynchronize(s));
+          i = st.halt_read + 1;
+          prev.valid = false;
+          continue;
+        }
+      }
+      if (!cur.valid) {
+        break;
+      }
+      prev = cur;
+      i = cur.next_i;
+      set ^= 1;
+    }
+  } else {
+    while (i < end && !c->sel_finished) {
+      uint64_t launched = 0, j = i;
       for (; j < end && launched < kChunk; ++j) {
         if (c->h_flags[j] & GRB_READ_PASS2) {
           launch_read(c, j, j - first, c->d_dec.p);
           ++launched;
         }
       }
-    }
-    GrbSelState st;
-    GRB_CUDA(c, cudaMemcpyAsync(&st, c->d_state, sizeof st, cudaMemcpyDeviceToHost, s));
-    GRB_CUDA(c, cudaStreamSynchronize(s));
-    c->kflush();
-    if (st.halt == 2) {
-      // a batch stopped early (vote-table slack exhausted): nothing to reset, start a new batch
-      // at the first read that was not committed
-      st.halt = 0;
-      GRB_CUDA(c, cudaMemcpyAsync(c->d_state, &st, sizeof st, cudaMemcpyHostToDevice, s));
+      GrbSelState st;
+      GRB_CUDA(c, cudaMemcpyAsync(&st, c->d_state, sizeof st, cudaMemcpyDeviceToHost, s));
       GRB_CUDA(c, cudaStreamSynchronize(s));
-      i = st.halt_read;
-      continue;
-    }
-    if (st.halt) {
-      if (st.n_snap && stats && n_stats && *n_stats < stats_cap) {
-        stats[(*n_stats)++] = st.snap;
+      c->kflush();
+      if (st.halt) {
+        if (st.n_snap && stats && n_stats && *n_stats < stats_cap) {
+          stats[(*n_stats)++] = st.snap;
+        }
+        if (st.finished) {
+          c->sel_finished = true;
+          stop_at = st.halt_read + 1;
+          break;
+        }
+        // rollover: reset_counts + reset_ID_vector, then resume after the read that triggered it
+        GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0, (c->filt.pop + 1) * sizeof(GrbSlot), s));
+        st.halt = 0;
+        st.n_snap = 0;
+        GRB_CUDA(c, cudaMemcpyAsync(c->d_state, &st, sizeof st, cudaMemcpyHostToDevice, s));
+        GRB_CUDA(c, cudaStreamSynchronize(s));
+        i = st.halt_read + 1;
+        continue;
       }
-      if (st.finished) {
-        c->sel_finished = true;
-        stop_at = st.halt_read + 1;
-        break;
-      }
-      // rollover: reset_counts + reset_ID_vector, then resume after the read that triggered it
-      GRB_CUDA(c, cudaMemsetAsync(c->filt.slots, 0,
-                                  (c->filt.pop + 1) * sizeof(GrbSlot), s));
-      st.halt = 0;
-      st.n_snap = 0;
-      GRB_CUDA(c, cudaMemcpyAsync(c->d_state, &st, sizeof st, cudaMemcpyHostToDevice, s));
-      GRB_CUDA(c, cudaStreamSynchronize(s));
-      i = st.halt_read + 1;
-      continue;
+      i = j;
     }
-    i = j;
   }
   GRB_CUDA(c, cudaMemcpyAsync(decisions, c->d_dec.p, count * sizeof(grb_decision),
                               cudaMemcpyDeviceToHost, s));
   c->toc();
+  c->kflush(); // toc() waited for the stream: every launch group's event pair is complete
   GRB_CUDA(c, cudaGetLastError());
   for (uint64_t r = first; r < end; ++r) {
     grb_decision& d = decisions[r - first];
