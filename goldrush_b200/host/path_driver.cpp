@@ -8,6 +8,7 @@
 #include "goldrush_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdarg>
@@ -129,6 +130,42 @@ next_record_start(const char* d, size_t n, size_t from)
     line = l1;
   }
   return n;
+}
+
+// fn(i) for i in [lo, hi) on `threads` plain std::threads, work handed out `grain` items at a time.
+// Used for the record assembly that runs beside pass 2 instead of an OpenMP region: libgomp's
+// workers spin at the end of every region (GOMP_SPINCOUNT), and on a host with four cores per rank
+// that spinning took the core of the thread that launches the kernels.
+template<class F>
+void
+parallel_for(int threads, int64_t lo, int64_t hi, int64_t grain, F fn)
+{
+  if (threads <= 1 || hi - lo <= grain) {
+    for (int64_t i = lo; i < hi; ++i) {
+      fn(i);
+    }
+    return;
+  }
+  std::atomic<int64_t> next(lo);
+  auto work = [&] {
+    while (true) {
+      const int64_t b = next.fetch_add(grain);
+      if (b >= hi) {
+        return;
+      }
+      for (int64_t i = b; i < std::min(hi, b + grain); ++i) {
+        fn(i);
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < threads; ++t) {
+    pool.emplace_back(work);
+  }
+  work();
+  for (std::thread& t : pool) {
+    t.join();
+  }
 }
 
 double
@@ -832,11 +869,9 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
       } else if (want_bytes && buf.size() < bytes) {
         buf.resize(bytes);
       }
-#pragma omp parallel num_threads(emit_threads)
       {
-        std::vector<char> local; // record scratch when nothing is written (digest only)
-#pragma omp for schedule(dynamic, 4)
-        for (int64_t ri = (int64_t)r0; ri < (int64_t)r1; ++ri) {
+        parallel_for(emit_threads, (int64_t)r0, (int64_t)r1, 4, [&](int64_t ri) {
+          thread_local std::vector<char> local; // record scratch when nothing is written (digest only)
           Rec& r = recs[ri];
           const grb_read_meta& m = meta[r.read];
           char* dst;
@@ -884,7 +919,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
           if (want_phred) {
             r.phred = (!r.trimmed && r.ql == m.qual_len) ? m.phred_total_sum : sum_phred_host(ql, r.ql, tab);
           }
-        }
+        });
       }
       for (size_t ri = r0; ri < r1; ++ri) {
         const Rec& r = recs[ri];
