@@ -342,8 +342,8 @@ struct grb_ctx
   // ---- multi-GPU (comm.cuh): the process-wide NCCL communicator, when this context's device is
   // the one it was created on and it spans more than one rank ----
   GrbComm* comm = nullptr;
-  bool shard_query = false;  // pass-2 query sharding: default on from 4 ranks, GRB_SHARD_QUERY=0|1
-                             // overrides (the exchange costs about what it saves)
+  bool shard_query = false;  // pass-2 query sharding: off unless GRB_SHARD_QUERY=1 (the
+                             // exchange costs what it saves)
   DevBuf<uint64_t> comm_tmp; // all-gather landing zone of the pass-1 OR-reduce
   int fail_nccl(ncclResult_t r, const char* what)
   {
@@ -687,10 +687,14 @@ grb_create(const grb_params* p, grb_ctx** out)
     const char* off = getenv("GRB_COMM");
     if (g.comm && g.world > 1 && g.device == c->device && !(off && strcmp(off, "0") == 0)) {
       c->comm = &g;
-      // measured on B200 (profiles/README.md): the all-gather of the per-tile results costs what
-      // the sharded query saves at 2 GPUs and a little less from 4 GPUs on
+      // Each batch's speculative query can be sharded over the ranks (GRB_SHARD_QUERY=1), but it is
+      // not the default: measured on B200 (profiles/README.md, round 2) the all-gather of the
+      // per-tile results costs what the sharded query saves at every N (cfg2, 8 GPUs: query 134 ->
+      // 23 ms, exchange 113 ms), and a collective inside every batch couples the ranks' launch threads:
+      // on a host with four cores per rank the human-scale run took 30.8 s end to end with the query
+      // sharded and 18.2 s with every rank querying the whole batch.
       const char* sq = getenv("GRB_SHARD_QUERY");
-      c->shard_query = sq ? strcmp(sq, "1") == 0 : g.world >= 4;
+      c->shard_query = sq ? strcmp(sq, "1") == 0 : false;
     }
   }
   if ((e = grb_pool_alloc((void**)&c->d_seed, sizeof(GrbSeedTables))) != cudaSuccess ||

@@ -241,13 +241,17 @@ int grb_insert_tiles(grb_ctx* ctx, uint64_t read_idx, uint32_t tile_start, uint3
  * A process-wide NCCL communicator, bound at run time (dlopen of libnccl.so.2; no link dependency).
  * Rank 0 calls grb_comm_unique_id and ships the 128 bytes to the other ranks by any means
  * (torch.distributed broadcast, MPI, a file); every rank then calls grb_comm_init on its device.
- * Contexts created afterwards on that device shard the two phases that shard:
+ * Contexts created afterwards on that device shard what shards:
+ *   grb_reads_ingest_fastq + grb_reads_allgather
+ *                        - each rank copies and decodes its own slice of the FASTQ, the packed
+ *                          read store travels over NVLink (grb_run_path does this by itself)
  *   grb_build_bitvector  - pass 1 over this rank's share of the reads + OR-reduce of the vectors
  *                          (replaces the OpenMP team of fill_bit_vector, goldrush_path.cpp:252-311)
- *   grb_select_reads     - the speculative query of each batch over this rank's share of its
- *                          tiles + all-gather of the per-tile results; the ordered commit is
- *                          replicated, so every rank returns the same decisions
- * and grb_run_path inherits both.  GRB_COMM=0 in the environment keeps contexts single-GPU.
+ *   grb_select_reads     - with GRB_SHARD_QUERY=1 the speculative query of each batch over this
+ *                          rank's share of its tiles + all-gather of the per-tile results (off by
+ *                          default: the exchange costs what it saves).  The ordered commit is
+ *                          replicated either way, so every rank returns the same decisions
+ * and grb_run_path inherits all of it.  GRB_COMM=0 in the environment keeps contexts single-GPU.
  * Errors of grb_comm_unique_id / grb_comm_init are reported by grb_last_error(NULL). */
 int grb_comm_unique_id(uint8_t* out128);
 int grb_comm_init(const uint8_t* id128, int rank, int world, int device);
