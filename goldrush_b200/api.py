@@ -188,6 +188,7 @@ def lib():
         "grb_synth_fastq": (vp, [P(SynthParams), u64, u64, P(u64)]),
         "grb_free_host": (None, [vp]),
         "grb_test_group_hash_host": (i32, [P(C.c_char_p), u32, C.c_char_p, sz, vp]),
+        "grb_test_next_record_start": (sz, [C.c_char_p, sz, sz]),
         "grb_test_decide_host": (i32, [u32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u64, u64, u64,
                                        P(u32), vp, vp, vp]),
     }

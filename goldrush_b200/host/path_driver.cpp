@@ -1181,6 +1181,12 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   return GRB_OK;
 }
 
+extern "C" size_t
+grb_test_next_record_start(const char* fastq, size_t n, size_t from)
+{
+  return next_record_start(fastq, n, from);
+}
+
 extern "C" int
 grb_run_path(const grb_run_options* o, const char* fastq, size_t fastq_len, grb_run_result* res,
              char* err, size_t err_cap)

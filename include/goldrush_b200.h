@@ -434,6 +434,11 @@ int grb_test_decide_host(uint32_t n_tiles, const uint32_t* best_id, const uint32
                          uint64_t assigned_max, uint32_t* ids_inserted, uint32_t* out_ids,
                          uint8_t* out_assigned, uint32_t* out_plan);
 
+/* ---- test hook: the record-boundary search grb_run_path uses to cut a FASTQ buffer into the ranks'
+ * shares (several GPUs): first byte >= from at which a record starts (a line beginning with '@'
+ * whose line after next begins with '+'), n if there is none.  Host only. ---- */
+size_t grb_test_next_record_start(const char* fastq, size_t n, size_t from);
+
 /* ---- test hook: the grouped half-hash code of csrc/nthash.cuh (what the query and fill kernels
  * inline) compiled for the host; out[frame * h + pattern], frames = n - k + 1, ACGT only.  Checked
  * against the oracle's SeedNtHash restatement by the CPU test suite.  Never called by the product. */

@@ -215,6 +215,34 @@ def test_meson_files_name_the_sources_the_makefile_builds():
         assert os.path.exists(os.path.join(root, n)), n
 
 
+def test_record_boundary_search_cuts_only_between_records():
+    """Several GPUs: each rank ingests bytes [cut(r), cut(r + 1)) of the FASTQ.  A cut must fall on a
+    record start even when quality lines begin with '@' or '+' (both are legal Phred characters)."""
+    rnd = random.Random(5)
+    recs = []
+    for i in range(300):
+        n = rnd.randint(1, 60)
+        seq = "".join(rnd.choice("ACGT") for _ in range(n))
+        first = rnd.choice("@+I5")  # qualities that look like a header or a separator
+        qual = first + "".join(rnd.choice("@+#5IJ") for _ in range(n - 1))
+        recs.append(f"@r{i} c\n{seq}\n+\n{qual}\n")
+    data = "".join(recs).encode()
+    starts, pos = set(), 0
+    for r in recs:
+        starts.add(pos)
+        pos += len(r)
+    L = grb.lib()
+    for frm in range(0, len(data), 7):
+        got = L.grb_test_next_record_start(data, len(data), frm)
+        want = min((s for s in starts if s >= frm), default=len(data))
+        assert got == want, (frm, got, want)
+    # every world size: the shares tile the input and each starts on a record
+    for world in (2, 3, 8):
+        cuts = [L.grb_test_next_record_start(data, len(data), len(data) * r // world) for r in range(world)]
+        cuts.append(len(data))
+        assert cuts[0] == 0 and cuts == sorted(cuts) and all(c in starts or c == len(data) for c in cuts)
+
+
 def test_synth_generator_is_deterministic_and_thread_independent():
     sp = grb.api.synth_params(50000, 3.0, 2000, 77)
     a = grb.synth_fastq(sp)
