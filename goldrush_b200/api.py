@@ -616,6 +616,17 @@ def free_host(p):
     lib().grb_free_host(p)
 
 
+def host_pin(ptr, nbytes):
+    """grb_host_pin: page-locks [ptr, ptr + nbytes) in 1 GiB pieces; returns the bytes now pinned."""
+    got = C.c_size_t()
+    lib().grb_host_pin(ptr, nbytes, C.byref(got))
+    return got.value
+
+
+def host_unpin(ptr, pinned_bytes):
+    lib().grb_host_unpin(ptr, pinned_bytes)
+
+
 def synth_fastq(sp, first=0, count=None) -> bytes:
     L = lib()
     if count is None:

@@ -224,11 +224,20 @@ k_pack(const uint8_t* __restrict__ buf, uint64_t chunk_base, grb_read_meta* __re
   }
 }
 
-// one thread per record: strictly left-to-right double sums (calc_phred_average.cpp:15-30)
-__global__ void
+// one thread per record: strictly left-to-right double sums (calc_phred_average.cpp:15-30).  The
+// additions of one read are a dependent chain by definition (the sum must round as the
+// reference's does); what can be saved is around them: the 10^(-q/10) table sits in shared memory
+// (a data-dependent index into __constant__ memory serialises the 32 lanes of a warp) and the
+// quality bytes arrive 16 at a time.
+__global__ void __launch_bounds__(64)
 k_phred(const uint8_t* __restrict__ buf, uint64_t chunk_base, grb_read_meta* __restrict__ meta,
         uint64_t n_rec)
 {
+  __shared__ double tab[256];
+  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) {
+    tab[i] = c_delog[i];
+  }
+  __syncthreads();
   const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n_rec) {
     return;
@@ -238,11 +247,28 @@ k_phred(const uint8_t* __restrict__ buf, uint64_t chunk_base, grb_read_meta* __r
   const uint32_t mark = n / 2 - 1; // n/2 - 1 in size_t never equals i < n when n < 2
   const bool has_mark = n >= 2;
   double total = 0.0, first = 0.0;
-  for (uint32_t i = 0; i < n; ++i) {
-    total += c_delog[__ldg(q + i)];
+  uint32_t i = 0;
+  auto step = [&](uint32_t byte) {
+    total += tab[byte];
     if (has_mark && i == mark) {
       first = total;
     }
+    ++i;
+  };
+  const uint32_t head = (uint32_t)((16 - ((uintptr_t)q & 15)) & 15);
+  while (i < n && i < head) {
+    step(__ldg(q + i));
+  }
+  while (i + 16 <= n) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(q + i));
+    const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      step((w[j >> 2] >> ((j & 3) * 8)) & 0xFFu);
+    }
+  }
+  while (i < n) {
+    step(__ldg(q + i));
   }
   meta[r].phred_first_half_sum = first;
   meta[r].phred_total_sum = total;

@@ -561,11 +561,16 @@ def test_full_size_config_matches_reference_digests(cfg):
     common = dict(kmer_size=22, weight=16, hash_num=3, tile_length=1000, block_size=10,
                   unassigned_min=5, assigned_max=1, occupancy=0.1, threshold=10, phred_delta=5,
                   ratio=0.9, genome_size=s["genome"], phred_min=fs["phred_min"], seed_preset=SEED22)
+    # page-locked in 1 GiB pieces (grb_host_pin): the ingest copies of cfg2's 6 GB cross five piece
+    # boundaries, and one cudaMemcpyAsync must not span two registrations
+    pinned = grb.api.host_pin(ptr, n)
+    assert pinned == n
     try:
         rs, rg = grb.run_two_stage(ptr, dict(common, max_paths=5, min_length=20000, silver_path=1),
                                    dict(common, min_length=0, silver_path=0), nbytes=n,
                                    input_path="(memory)", write_outputs=False)
     finally:
+        grb.api.host_unpin(ptr, pinned)
         grb.free_host(ptr)
     for res, ref in ((rs, fs["silver"]), (rg, fs["golden"])):
         assert res.out_digest == ref["out_digest"]
