@@ -516,8 +516,8 @@ class Engine:
     def commit_profile(self):
         out = (C.c_uint64 * 10)()
         self._chk(self._L.grb_commit_profile(self._h, out))
-        names = ["check_cyc", "plans_changed", "resmooth_cyc", "decide_cyc", "insert_cyc",
-                 "conflict_frames", "reads", "resmoothed", "inserted", "checked"]
+        names = ["walk_cyc", "scans_with_a_changed_plan", "revalidate_cyc", "wait_and_scan_cyc",
+                 "final_cyc", "conflict_frames", "reads", "iterations", "reads_inserting", "batches"]
         return dict(zip(names, [int(x) for x in out]))
 
     def kernel_time(self, kclass):

@@ -175,10 +175,6 @@ grb_grid_barrier(unsigned long long* ctr, unsigned long long target)
   __syncthreads();
 }
 
-// Shared-memory carve-up of k_commit_batch:
-//   uint32 fbits[fb_words] dkeys[table_size] dvals[table_size] ukeys[us] uvals[us] oldrow[us]
-//   | uint32 best_id[n_cap] best_cnt[n_cap] root[n_cap] uq[n_cap] tile_id[n_cap] snap[n_cap + 2]
-
 // (tile, frame, pattern) of a stash index, and whether it is a valid (non-stale) position of its
 // pattern: multiLensfrHashIterator.hpp:49-68 repeats the last value of an exhausted pattern, and
 // insertMIBF de-duplicates it away (MIBFConstructSupport.hpp:255-270)

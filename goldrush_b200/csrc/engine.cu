@@ -2360,7 +2360,7 @@ struct BatchPlan
 
 // ---- batch engine: query-side buffers ------------------------------------------------------
 static int
-batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, uint64_t max_cm_words,
+query_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, uint64_t max_cm_words,
                uint32_t max_batch_reads)
 {
   cudaStream_t s = c->stream;
@@ -2436,12 +2436,12 @@ batch2_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
 static const uint32_t kFixDeltaSmem = 8192; // shared-memory delta table entries of k3_fix
 
 static int
-batch3_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, uint64_t max_cm_words,
+commit_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, uint64_t max_cm_words,
                uint32_t max_batch_reads)
 {
   cudaStream_t s = c->stream;
   const uint64_t T = c->tile_frames, h = c->h_seed.h; // T: frames per tile
-  int rc = batch2_prepare(c, max_batch_tiles, max_read_tiles, max_cm_words, max_batch_reads);
+  int rc = query_prepare(c, max_batch_tiles, max_read_tiles, max_cm_words, max_batch_reads);
   if (rc != GRB_OK) {
     return rc;
   }
@@ -2509,7 +2509,7 @@ batch3_prepare(grb_ctx* c, uint64_t max_batch_tiles, uint64_t max_read_tiles, ui
 }
 
 static int
-launch_batch3(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
+launch_batch(grb_ctx* c, const BatchPlan::Batch& b, grb_decision* d_dec)
 {
   cudaStream_t s = c->stream;
   const uint64_t T = c->tile_frames, h = c->h_seed.h; // T: frames per tile
@@ -2814,7 +2814,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
         bp.tile_first.push_back(bp.batches.back().n_bt);
         // with W ranks every per-tile buffer holds W equal shares (the last one padded)
         const uint64_t pad_bt = (c->comm && c->shard_query) ? (uint64_t)c->comm->world : 0;
-        rc = batch3_prepare(c, std::max<uint64_t>(max_bt, 1) + pad_bt, max_len / T, max_cm, max_nb);
+        rc = commit_prepare(c, std::max<uint64_t>(max_bt, 1) + pad_bt, max_len / T, max_cm, max_nb);
         if (rc != GRB_OK) {
           return rc;
         }
@@ -2836,7 +2836,7 @@ grb_select_reads(grb_ctx* c, uint64_t first, uint64_t count, grb_decision* decis
                                       bp.tile_read.size() * 4, cudaMemcpyHostToDevice, s));
         }
         for (const BatchPlan::Batch& b : bp.batches) {
-          rc = launch_batch3(c, b, c->d_dec.p);
+          rc = launch_batch(c, b, c->d_dec.p);
           if (rc != GRB_OK) {
             return rc;
           }

@@ -1,4 +1,4 @@
-// Batch engine of the pass-2 loop, third generation: the ordered commit as a parallel fixed point.
+// Batch engine of the pass-2 loop: the ordered commit as a parallel fixed point.
 //
 // Replaces the same reference code as kernels_select.cuh (goldrush_path.cpp:529-890
 // calc_num_assigned_tiles, :892-1094 process_read, :156-187 silver_path_check,

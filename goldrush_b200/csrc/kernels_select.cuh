@@ -39,9 +39,9 @@ struct GrbSelState
   uint64_t curr_path;
   grb_path_stats cur;
   grb_path_stats snap; // counters at the last rollover (log_path_stat, :126-154)
-  // k_commit_batch phase clocks of CTA 0 (SM cycles) and event counts, for grb_commit_profile:
-  // 0 check, 1 barrier after check, 2 re-smoothing (+ its barrier), 3 decide, 4 insert,
-  // 5 barrier after insert, 6 reads, 7 reads re-smoothed, 8 reads inserted, 9 reads checked
+  // k3_fix phase clocks of CTA 0 (SM cycles) and event counts, for grb_commit_profile: 0 walk,
+  // 2 re-validation of its reads, 3 wait for the slowest CTA + order scan, 4 final pass; 1 scans that
+  // found a plan contradicted, 5 conflict frames, 6 reads, 7 iterations, 8 inserting reads, 9 batches
   unsigned long long prof[10];
 };
 

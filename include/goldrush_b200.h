@@ -299,21 +299,26 @@ int grb_stream(grb_ctx* ctx, void** cuda_stream);
  * grb_profile_enable (which also resets them).  Used by bench.py for the roofline. */
 typedef enum grb_kernel_class
 {
-  GRB_K_FILL = 0,   /* K2+K4a  k_fill_bits */
+  GRB_K_FILL = 0,   /* K2+K4a  k_fill_part + k_fill_apply (or k_fill_bits, the direct form) */
   GRB_K_RANK = 1,   /* K4b     k_rank_partial + k_scan_u32 + k_rank_write */
-  GRB_K_QUERY = 2,  /* K2+K3   k_spec_query (batch engine) / k_query (serial engine) */
-  GRB_K_DECIDE = 3, /*         k_decide (serial engine) */
-  GRB_K_INSERT = 4, /* K4c     k_insert_collect + k_insert_apply (serial engine) */
-  GRB_K_SMOOTH = 5, /*         k_spec_cmat: count matrix + smoothing on the speculative votes */
-  GRB_K_DEDUPE = 6, /*         k_spec_dedupe: distinct ranks per read for the insert */
-  GRB_K_COMMIT = 7, /* K4c     k_commit_batch: ordered re-validation, decision and insert */
+  GRB_K_QUERY = 2,  /* K2+K3   k2_query (batch engine) / k_query (serial engine) */
+  GRB_K_DECIDE = 3, /*         k_decide (serial engine only) */
+  GRB_K_INSERT = 4, /* K4c     k3_bulk: reservoir inserts of the private ranks + write-back of the
+                               shared ones (serial engine: k_insert_collect + k_insert_apply) */
+  GRB_K_SMOOTH = 5, /*         k2_cmat: count matrix + smoothing + plan on the speculative votes */
+  GRB_K_DEDUPE = 6, /*         the batch index: k3_mark ... k3_frames (which ranks do two probes of
+                               the batch share, member lists, conflict-frame records) */
+  GRB_K_COMMIT = 7, /* K4c     k3_fix: the ordered commit as a parallel fixed point */
   GRB_K_GATHER = 8, /*         multi-GPU exchange: NCCL all-gathers + k_or_gathered (0 on one GPU) */
   GRB_K_COUNT = 9
 } grb_kernel_class;
 int grb_profile_enable(grb_ctx* ctx, int on);
-/* phase clocks of the ordered commit kernel since the last grb_filter_alloc, as counted by its
- * CTA 0: out[0..5] = SM cycles in check, barrier, re-smoothing, decide, insert, barrier;
- * out[6..9] = reads committed, re-smoothed, inserted, re-validated. */
+/* Phase clocks of the ordered commit kernel (k3_fix) since the loop state was created, as counted
+ * by its CTA 0, each including the grid barrier in front of it: out[0] = SM cycles walking the
+ * shared ranks' histories, out[2] = re-validating its share of the reads, out[3] = waiting for the
+ * slowest CTA's reads + the in-order scan, out[4] = decisions and counters of the committed reads;
+ * out[1] = scans that found a plan contradicted, out[5] = conflict frames, out[6] = reads committed,
+ * out[7] = fixed-point iterations, out[8] = reads that inserted, out[9] = batches. */
 int grb_commit_profile(grb_ctx* ctx, uint64_t* out10);
 int grb_kernel_time(grb_ctx* ctx, int kclass, double* ms, uint64_t* n_launches);
 
