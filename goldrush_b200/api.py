@@ -87,6 +87,10 @@ class RunResult(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class HostMsg(C.Structure):
+    _fields_ = [("peer", C.c_int32), ("pad", C.c_int32), ("ptr", C.c_void_p), ("bytes", C.c_uint64)]
+
+
 class SynthParams(C.Structure):
     _fields_ = [
         ("genome_len", C.c_uint64), ("seed", C.c_uint64), ("coverage", C.c_double),
@@ -189,6 +193,8 @@ def lib():
         "grb_free_host": (None, [vp]),
         "grb_test_group_hash_host": (i32, [P(C.c_char_p), u32, C.c_char_p, sz, vp]),
         "grb_test_next_record_start": (sz, [C.c_char_p, sz, sz]),
+        "grb_abi_sizes": (None, [vp]),
+        "grb_test_plan_silver_parts": (i32, [vp, u32, C.c_int32, vp, vp]),
         "grb_test_decide_host": (i32, [u32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u64, u64, u64,
                                        P(u32), vp, vp, vp]),
     }

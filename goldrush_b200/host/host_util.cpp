@@ -82,6 +82,20 @@ grb_phred_finalize(double first_half_sum, double total_sum, uint64_t n, uint32_t
   *delta = (uint32_t)abs((int32_t)(-10 * log10(first_avg)) - (int32_t)(-10 * log10(second_avg)));
 }
 
+void
+grb_abi_sizes(uint64_t* out9)
+{
+  out9[0] = sizeof(grb_params);
+  out9[1] = sizeof(grb_read_meta);
+  out9[2] = sizeof(grb_decision);
+  out9[3] = sizeof(grb_path_stats);
+  out9[4] = sizeof(grb_probe_bench_result);
+  out9[5] = sizeof(grb_run_options);
+  out9[6] = sizeof(grb_run_result);
+  out9[7] = sizeof(grb_synth_params);
+  out9[8] = sizeof(grb_host_msg);
+}
+
 // the same for n reads at once (host threads), from the metadata K1 returned
 void
 grb_phred_finalize_batch(const grb_read_meta* meta, uint64_t n, uint32_t* avg, uint32_t* delta)

@@ -168,6 +168,46 @@ parallel_for(int threads, int64_t lo, int64_t hi, int64_t grain, F fn)
   }
 }
 
+// Two-stage call in slice mode: the joined silver paths are a sequence of parts (path q, rank r) --
+// q in the order of `order` (the shell glob's), r in rank order; part (q, r) holds bytes[r * n_paths
+// + q] bytes on rank r.  Each golden-stage rank gets a run of whole, consecutive parts of about
+// total / ranks bytes: to[i] = receiving rank of the i-th part of that sequence (non-decreasing).
+// Returns false if some rank would get nothing (the caller then gathers everything everywhere).
+bool
+plan_silver_parts(const std::vector<uint64_t>& bytes, size_t n_paths, int ranks,
+                  const std::vector<size_t>& order, std::vector<int>* to, std::vector<uint64_t>* got)
+{
+  uint64_t total = 0;
+  for (uint64_t v : bytes) {
+    total += v;
+  }
+  to->clear();
+  got->assign((size_t)ranks, 0);
+  if (total == 0) {
+    return false;
+  }
+  uint64_t start = 0;
+  int prev = 0;
+  for (size_t q : order) {
+    for (int r = 0; r < ranks; ++r) {
+      const uint64_t b = bytes[(size_t)r * n_paths + q];
+      int t = (int)std::min<uint64_t>((uint64_t)ranks - 1,
+                                      (uint64_t)((unsigned __int128)(start + b / 2) * (unsigned)ranks / total));
+      t = std::max(t, prev);
+      prev = t;
+      to->push_back(t);
+      (*got)[(size_t)t] += b;
+      start += b;
+    }
+  }
+  for (uint64_t v : *got) {
+    if (v == 0) {
+      return false;
+    }
+  }
+  return true;
+}
+
 double
 now_ms()
 {
@@ -1089,27 +1129,16 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
         int to;
       };
       std::vector<Part> parts;
+      std::vector<int> to;
+      std::vector<uint64_t> got;
+      const bool all_fed = plan_silver_parts(all, n_paths, ranks, order, &to, &got);
       uint64_t cum = 0;
       for (size_t q : order) {
         for (int r = 0; r < ranks; ++r) {
           const uint64_t b = all[(size_t)r * n_paths + q];
-          parts.push_back(Part{ q, r, cum, b, 0 });
+          parts.push_back(Part{ q, r, cum, b, to.empty() ? 0 : to[parts.size()] });
           cum += b;
         }
-      }
-      std::vector<uint64_t> got((size_t)ranks, 0);
-      int prev = 0;
-      for (Part& pt : parts) {
-        int to = (int)std::min<uint64_t>((uint64_t)ranks - 1,
-                                         (uint64_t)((unsigned __int128)(pt.start + pt.bytes / 2) * (unsigned)ranks / total));
-        to = std::max(to, prev);
-        prev = to;
-        pt.to = to;
-        got[(size_t)to] += pt.bytes;
-      }
-      bool all_fed = true;
-      for (uint64_t v : got) {
-        all_fed = all_fed && v > 0;
       }
       if (all_fed) {
         int me = 0, w = 1;
@@ -1179,6 +1208,29 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     *res = R;
   }
   return GRB_OK;
+}
+
+extern "C" int
+grb_test_plan_silver_parts(const uint64_t* bytes, uint32_t n_paths, int32_t ranks, int32_t* to,
+                           uint64_t* got)
+{
+  std::vector<uint64_t> b(bytes, bytes + (size_t)n_paths * ranks), g;
+  std::vector<size_t> order(n_paths);
+  for (size_t i = 0; i < order.size(); ++i) {
+    order[i] = i;
+  }
+  std::sort(order.begin(), order.end(), [](size_t x, size_t y) {
+    return std::to_string(x + 1) + ".fq" < std::to_string(y + 1) + ".fq";
+  });
+  std::vector<int> t;
+  const bool ok = plan_silver_parts(b, n_paths, ranks, order, &t, &g);
+  for (size_t i = 0; i < t.size(); ++i) {
+    to[i] = t[i];
+  }
+  for (size_t i = 0; i < g.size(); ++i) {
+    got[i] = g[i];
+  }
+  return ok ? 1 : 0;
 }
 
 extern "C" size_t

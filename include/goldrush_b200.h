@@ -439,10 +439,21 @@ int grb_test_decide_host(uint32_t n_tiles, const uint32_t* best_id, const uint32
                          uint64_t assigned_max, uint32_t* ids_inserted, uint32_t* out_ids,
                          uint8_t* out_assigned, uint32_t* out_plan);
 
+/* ---- test hook: sizeof of every struct that crosses this ABI, in declaration order (grb_params,
+ * grb_read_meta, grb_decision, grb_path_stats, grb_probe_bench_result, grb_run_options,
+ * grb_run_result, grb_synth_params, grb_host_msg), so that a binding can check its mirror. ---- */
+void grb_abi_sizes(uint64_t* out9);
+
 /* ---- test hook: the record-boundary search grb_run_path uses to cut a FASTQ buffer into the ranks'
  * shares (several GPUs): first byte >= from at which a record starts (a line beginning with '@'
  * whose line after next begins with '+'), n if there is none.  Host only. ---- */
 size_t grb_test_next_record_start(const char* fastq, size_t n, size_t from);
+/* ---- test hook: grb_run_two_stage in slice mode hands the silver records to the golden stage's
+ * ranks in whole parts (path q of rank r = bytes[r * n_paths + q]), paths in shell-glob order, ranks
+ * in rank order: to[n_paths * ranks] = receiving rank of each part of that sequence, got[ranks] =
+ * bytes per receiving rank; returns 0 if some rank would get nothing.  Host only. ---- */
+int grb_test_plan_silver_parts(const uint64_t* bytes, uint32_t n_paths, int32_t ranks, int32_t* to,
+                               uint64_t* got);
 
 /* ---- test hook: the grouped half-hash code of csrc/nthash.cuh (what the query and fill kernels
  * inline) compiled for the host; out[frame * h + pattern], frames = n - k + 1, ACGT only.  Checked

@@ -27,6 +27,19 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L._grb_symbols), "ctypes mirror out of sync with the header"
 
 
+def test_ctypes_mirror_has_the_sizes_of_the_c_structs():
+    """goldrush_b200/api.py mirrors include/goldrush_b200.h by hand: every struct that crosses the ABI
+    must have the size (and the numpy dtypes the itemsize) the library was compiled with."""
+    out = (C.c_uint64 * 9)()
+    grb.lib().grb_abi_sizes(out)
+    A = grb.api
+    mirrors = [A.Params, A.ReadMeta, A.Decision, A.PathStats, A.ProbeBenchResult, A.RunOptions,
+               A.RunResult, A.SynthParams, A.HostMsg]
+    assert [int(x) for x in out] == [C.sizeof(m) for m in mirrors]
+    assert A.READ_META_DTYPE.itemsize == C.sizeof(A.ReadMeta)
+    assert A.DECISION_DTYPE.itemsize == C.sizeof(A.Decision)
+
+
 def test_seed_pattern_kats():
     # SURVEY.md 8(a) A2: strings printed by the reference's make_seed_pattern in this image (glibc rand)
     assert grb.make_seed_pattern("", 22, 16, 3) == [
@@ -241,6 +254,35 @@ def test_record_boundary_search_cuts_only_between_records():
         cuts = [L.grb_test_next_record_start(data, len(data), len(data) * r // world) for r in range(world)]
         cuts.append(len(data))
         assert cuts[0] == 0 and cuts == sorted(cuts) and all(c in starts or c == len(data) for c in cuts)
+
+
+def test_silver_parts_reach_the_golden_ranks_in_order_and_in_balance():
+    """grb_run_two_stage, slice mode: every (path, rank) part of the silver output goes whole to one
+    golden-stage rank; receiving ranks never decrease along the joined stream (so each rank's share is
+    one consecutive slice of it), every byte is delivered once, and with equal shares per path the
+    ranks end up within one part of total / ranks."""
+    L = grb.lib()
+    rnd = random.Random(9)
+    for n_paths, ranks in ((5, 8), (2, 2), (12, 4), (1, 8), (3, 3)):
+        sizes = np.array([[rnd.randint(900, 1100) for _ in range(n_paths)] for _ in range(ranks)],
+                         dtype=np.uint64)
+        to = np.zeros(n_paths * ranks, dtype=np.int32)
+        got = np.zeros(ranks, dtype=np.uint64)
+        ok = L.grb_test_plan_silver_parts(sizes.ctypes.data, n_paths, ranks, to.ctypes.data, got.ctypes.data)
+        assert ok == 1
+        assert (np.diff(to) >= 0).all() and to[0] == 0 and to[-1] == ranks - 1
+        assert int(got.sum()) == int(sizes.sum())
+        # the sequence is path-major in shell-glob order (_1, _10, _11, _12, _2, ...), rank-minor
+        order = sorted(range(n_paths), key=lambda q: f"{q + 1}.fq")
+        seq = [int(sizes[r][q]) for q in order for r in range(ranks)]
+        per = [sum(b for b, t in zip(seq, to) if t == g) for g in range(ranks)]
+        assert per == [int(x) for x in got]
+        assert max(per) - min(per) <= 2 * 1100
+    # one rank holds everything and there is a single path: nothing to hand to the others
+    sizes = np.array([[5000], [0], [0]], dtype=np.uint64)
+    to = np.zeros(3, dtype=np.int32)
+    got = np.zeros(3, dtype=np.uint64)
+    assert L.grb_test_plan_silver_parts(sizes.ctypes.data, 1, 3, to.ctypes.data, got.ctypes.data) == 0
 
 
 def test_synth_generator_is_deterministic_and_thread_independent():
