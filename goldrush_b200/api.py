@@ -87,6 +87,11 @@ class RunResult(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class PolishParams(C.Structure):
+    _fields_ = [("hash_num", C.c_uint32), ("n_k", C.c_uint32), ("k_values", C.POINTER(C.c_uint32)),
+                ("cbf_bytes", C.c_uint64), ("bf_bytes", C.c_uint64)]
+
+
 class HostMsg(C.Structure):
     _fields_ = [("peer", C.c_int32), ("pad", C.c_int32), ("ptr", C.c_void_p), ("bytes", C.c_uint64)]
 
@@ -194,6 +199,10 @@ def lib():
         "grb_test_group_hash_host": (i32, [P(C.c_char_p), u32, C.c_char_p, sz, vp]),
         "grb_test_next_record_start": (sz, [C.c_char_p, sz, sz]),
         "grb_abi_sizes": (None, [vp]),
+        "grb_polish_kmer_threshold": (i32, [u64]),
+        "grb_polish_plan_target": (i32, [u64, dbl, u32, P(C.c_char_p), vp, vp, vp, P(u32), P(C.c_int32)]),
+        "grb_polish_fill_batches": (i32, [vp, P(PolishParams), u32, vp, C.c_char_p, vp, vp, vp]),
+        "grb_test_polish_fill_host": (i32, [P(PolishParams), u32, vp, C.c_char_p, vp, vp, vp]),
         "grb_test_plan_silver_parts": (i32, [vp, u32, C.c_int32, vp, vp]),
         "grb_test_decide_host": (i32, [u32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u64, u64, u64,
                                        P(u32), vp, vp, vp]),
@@ -340,6 +349,14 @@ class Engine:
 
     def reads_count(self):
         return self._L.grb_reads_count(self._h)
+
+    def polish_fill_batches(self, params, batches):
+        """grb_polish_fill_batches: Bloom filters [batch][k index][bf_bytes] of the batches' reads."""
+        seqs, off, thr, first = _polish_inputs(batches)
+        out = np.zeros(max(1, len(batches) * params.n_k * params.bf_bytes), dtype=np.uint8)
+        self._chk(self._L.grb_polish_fill_batches(self._h, C.byref(params), len(batches), _ptr(first), seqs,
+                                                  _ptr(off), _ptr(thr), _ptr(out)))
+        return out.reshape(len(batches), params.n_k, params.bf_bytes)
 
     def reads_set_origin(self, byte_offset):
         self._chk(self._L.grb_reads_set_origin(self._h, int(byte_offset)))
@@ -620,6 +637,52 @@ def synth_fastq_raw(sp, first=0, count=None):
 
 def free_host(p):
     lib().grb_free_host(p)
+
+
+# ---- (f4) GoldPolish targeted Bloom filters ----
+def polish_params(k_values, hash_num=4, cbf_bytes=10 << 20, bf_bytes=512 << 10):
+    ks = np.ascontiguousarray(k_values, dtype=np.uint32)
+    p = PolishParams(hash_num, len(ks), ks.ctypes.data_as(C.POINTER(C.c_uint32)), cbf_bytes, bf_bytes)
+    p._keep = ks
+    return p
+
+
+def polish_plan_target(target_len, subsample_max_per_10kbp, ids, phred_avg, lens):
+    """grb_polish_plan_target: (order, n_used, kmer_threshold) of one target's mapped reads."""
+    n = len(ids)
+    arr = (C.c_char_p * n)(*[i.encode() for i in ids])
+    ph = np.ascontiguousarray(phred_avg, dtype=np.float64)
+    ln = np.ascontiguousarray(lens, dtype=np.uint64)
+    order = np.zeros(max(1, n), dtype=np.uint32)
+    used, thr = C.c_uint32(), C.c_int32()
+    rc = lib().grb_polish_plan_target(int(target_len), float(subsample_max_per_10kbp), n, arr, _ptr(ph),
+                                      _ptr(ln), _ptr(order), C.byref(used), C.byref(thr))
+    if rc:
+        raise GrbError(rc, "grb_polish_plan_target")
+    return order[:n], used.value, thr.value
+
+
+def _polish_inputs(batches):
+    """batches: list of lists of (sequence bytes, threshold) in insertion order."""
+    seqs, off, thr, first = [], [0], [], [0]
+    for b in batches:
+        for s, t in b:
+            seqs.append(s)
+            off.append(off[-1] + len(s))
+            thr.append(t)
+        first.append(len(thr))
+    return (b"".join(seqs), np.array(off, dtype=np.uint64), np.array(thr + [0], dtype=np.uint32),
+            np.array(first, dtype=np.uint64))
+
+
+def polish_fill_host(params, batches):
+    seqs, off, thr, first = _polish_inputs(batches)
+    out = np.zeros(max(1, len(batches) * params.n_k * params.bf_bytes), dtype=np.uint8)
+    rc = lib().grb_test_polish_fill_host(C.byref(params), len(batches), _ptr(first), seqs, _ptr(off),
+                                         _ptr(thr), _ptr(out))
+    if rc:
+        raise GrbError(rc, "grb_test_polish_fill_host")
+    return out.reshape(len(batches), params.n_k, params.bf_bytes)
 
 
 def host_pin(ptr, nbytes):

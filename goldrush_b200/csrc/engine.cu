@@ -10,6 +10,7 @@
 #include "kernels_commit.cuh"
 #include "comm.cuh"
 #include "kernels_probe.cuh"
+#include "kernels_polish.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1372,6 +1373,90 @@ grb_comm_allgather_host(grb_ctx* c, const void* send, uint64_t n, void* out, uin
     at += cnt[q];
   }
   GRB_CUDA(c, cudaStreamSynchronize(s));
+  return GRB_OK;
+}
+
+// (f4) GoldPolish targeted Bloom filters: jobs = (batch, k) pairs, run in waves sized to the device
+// memory their counting filters need (10 MiB each in the reference)
+int
+grb_polish_fill_batches(grb_ctx* c, const grb_polish_params* p, uint32_t n_batches,
+                        const uint64_t* batch_first, const char* seqs, const uint64_t* seq_off,
+                        const uint32_t* thresholds, uint8_t* out_bfs)
+{
+  cudaSetDevice(c->device);
+  if (!p || p->n_k == 0 || p->hash_num == 0 || p->hash_num > 8 || p->cbf_bytes < 2 || p->bf_bytes < 1) {
+    return c->fail(GRB_ERR_ARG, "grb_polish_fill_batches: n_k, hash_num in 1..8, cbf_bytes >= 2, bf_bytes >= 1");
+  }
+  if (n_batches == 0) {
+    return GRB_OK;
+  }
+  cudaStream_t s = c->stream;
+  const uint64_t n_reads = batch_first[n_batches];
+  const uint64_t n_bytes = seq_off[n_reads];
+  for (uint64_t r = 0; r < n_reads; ++r) {
+    if (thresholds[r] < 4) { // utils.cpp:105-107
+      return c->fail(GRB_ERR_ARG, "grb_polish_fill_batches: kmer_threshold must be greater than or equal to 4");
+    }
+  }
+  DevBuf<char> d_seqs;
+  DevBuf<uint64_t> d_off, d_first;
+  DevBuf<uint32_t> d_thr, d_k;
+  DevBuf<int> d_status;
+  GRB_CUDA(c, d_seqs.reserve_exact(std::max<uint64_t>(n_bytes, 1), s));
+  GRB_CUDA(c, d_off.reserve_exact(n_reads + 1, s));
+  GRB_CUDA(c, d_first.reserve_exact((uint64_t)n_batches + 1, s));
+  GRB_CUDA(c, d_thr.reserve_exact(std::max<uint64_t>(n_reads, 1), s));
+  GRB_CUDA(c, d_k.reserve_exact(p->n_k, s));
+  GRB_CUDA(c, d_status.reserve_exact(1, s));
+  GRB_CUDA(c, cudaMemcpyAsync(d_seqs.p, seqs, n_bytes, cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemcpyAsync(d_off.p, seq_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemcpyAsync(d_first.p, batch_first, ((uint64_t)n_batches + 1) * 8, cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemcpyAsync(d_thr.p, thresholds, n_reads * 4, cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemcpyAsync(d_k.p, p->k_values, (uint64_t)p->n_k * 4, cudaMemcpyHostToDevice, s));
+  GRB_CUDA(c, cudaMemsetAsync(d_status.p, 0, 4, s));
+  size_t free_b = 0, total_b = 0;
+  GRB_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  const uint64_t per_job = p->cbf_bytes + p->bf_bytes;
+  const uint64_t n_jobs = (uint64_t)n_batches * p->n_k;
+  const uint64_t budget = std::min<uint64_t>(free_b / 2, (uint64_t)32 << 30);
+  const uint64_t wave = std::max<uint64_t>(1, std::min<uint64_t>(n_jobs, budget / per_job));
+  DevBuf<uint8_t> d_cbf, d_bf;
+  GRB_CUDA(c, d_cbf.reserve_exact(wave * p->cbf_bytes, s));
+  GRB_CUDA(c, d_bf.reserve_exact(wave * p->bf_bytes, s));
+  c->tic();
+  for (uint64_t j0 = 0; j0 < n_jobs; j0 += wave) {
+    const uint64_t n = std::min(wave, n_jobs - j0);
+    GRB_CUDA(c, cudaMemsetAsync(d_cbf.p, 0, n * p->cbf_bytes, s));
+    GRB_CUDA(c, cudaMemsetAsync(d_bf.p, 0, n * p->bf_bytes, s));
+    GrbPolishWave w;
+    w.seqs = d_seqs.p;
+    w.off = d_off.p;
+    w.thr = d_thr.p;
+    w.batch_first = d_first.p;
+    w.k_values = d_k.p;
+    w.n_k = p->n_k;
+    w.hash_num = p->hash_num;
+    w.job0 = (uint32_t)j0;
+    w.n_jobs = (uint32_t)n;
+    w.cbf = d_cbf.p;
+    w.bf = d_bf.p;
+    w.cbf_bytes = p->cbf_bytes;
+    w.cbf_inv = (uint64_t)(((unsigned __int128)1 << 64) / p->cbf_bytes);
+    w.bf_bytes = p->bf_bytes;
+    w.bf_inv = (uint64_t)(((unsigned __int128)1 << 64) / (p->bf_bytes * 8));
+    w.status = d_status.p;
+    k_polish_fill<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(w);
+    c->launches += 1;
+    GRB_CUDA(c, cudaMemcpyAsync(out_bfs + j0 * p->bf_bytes, d_bf.p, n * p->bf_bytes, cudaMemcpyDeviceToHost, s));
+    GRB_CUDA(c, cudaStreamSynchronize(s));
+  }
+  c->toc();
+  int status = 0;
+  GRB_CUDA(c, cudaMemcpy(&status, d_status.p, 4, cudaMemcpyDeviceToHost));
+  GRB_CUDA(c, cudaGetLastError());
+  if (status != 0) {
+    return c->fail(GRB_ERR_ARG, "grb_polish_fill_batches: a job refused its input");
+  }
   return GRB_OK;
 }
 

@@ -412,6 +412,44 @@ int grb_run_two_stage(const grb_run_options* silver, const grb_run_options* gold
                       const char* fastq, size_t fastq_len, grb_run_result* res_silver,
                       grb_run_result* res_golden, char* err, size_t err_cap);
 
+/* ---- (f4) GoldPolish targeted Bloom filters ----
+ * The computational core of goldpolish-targeted-bfs (subprojects/goldpolish/src/
+ * goldpolish_targeted_bfs.cpp:53-149 serve_batch, utils.cpp:96-123 fill_bfs): per batch of target
+ * sequences and per k value, every k-mer of the mapped reads goes, in order, through a counting
+ * Bloom filter and into a plain Bloom filter once its count reaches the target's threshold.  The
+ * named-pipe protocol, the sequence / mapping index files and the .bf file header stay on the
+ * caller's side (control plane).  hash_num = 4, cbf_bytes = 10 MiB, bf_bytes = 512 KiB in the
+ * reference (:261-263). */
+typedef struct grb_polish_params
+{
+  uint32_t hash_num;
+  uint32_t n_k;
+  const uint32_t* k_values; /* one Bloom filter per k per batch ("k<k>.bf", :217-221) */
+  uint64_t cbf_bytes;
+  uint64_t bf_bytes;
+} grb_polish_params;
+/* goldpolish_targeted_bfs.cpp:43-51 mappings_bases_to_kmer_threshold */
+int grb_polish_kmer_threshold(uint64_t mappings_bases);
+/* What serve_batch derives for one target (:88-127): its mapped reads sorted by (Phred average as
+ * size_t descending, id ascending), the first min(n, target_len * subsample_max_per_10kbp / 10000)
+ * of them used, the k-mer threshold from their total length.  order_out[n_mappings] = indices into
+ * the inputs in sorted order, *n_used = how many of them are inserted.  Host only. */
+int grb_polish_plan_target(uint64_t target_len, double subsample_max_per_10kbp, uint32_t n_mappings,
+                           const char* const* ids, const double* phred_avg, const uint64_t* lens,
+                           uint32_t* order_out, uint32_t* n_used, int32_t* kmer_threshold);
+/* fill_bfs over every batch: batch b = reads [batch_first[b], batch_first[b + 1]) in serve_batch's
+ * order, read r = seqs[seq_off[r], seq_off[r + 1]) (HOST memory) inserted with thresholds[r] (its
+ * target's k-mer threshold, >= 4).  out_bfs[(b * n_k + i) * bf_bytes ...] = the Bloom filter of
+ * batch b and k_values[i], raw bit array (bit of hash h = h % (8 * bf_bytes), LSB first). */
+int grb_polish_fill_batches(grb_ctx* ctx, const grb_polish_params* p, uint32_t n_batches,
+                            const uint64_t* batch_first, const char* seqs, const uint64_t* seq_off,
+                            const uint32_t* thresholds, uint8_t* out_bfs);
+/* test hook: the same jobs (csrc/polish_core.h, one code for host and device) run on the host, for
+ * CPU-side checks against the oracle.  Never called by the product path. */
+int grb_test_polish_fill_host(const grb_polish_params* p, uint32_t n_batches, const uint64_t* batch_first,
+                              const char* seqs, const uint64_t* seq_off, const uint32_t* thresholds,
+                              uint8_t* out_bfs);
+
 /* ---- synthetic reads; host only, used by bench.py and the tests ---- */
 typedef struct grb_synth_params
 {
