@@ -1418,7 +1418,9 @@ grb_polish_fill_batches(grb_ctx* c, const grb_polish_params* p, uint32_t n_batch
   GRB_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   const uint64_t per_job = p->cbf_bytes + p->bf_bytes;
   const uint64_t n_jobs = (uint64_t)n_batches * p->n_k;
-  const uint64_t budget = std::min<uint64_t>(free_b / 2, (uint64_t)32 << 30);
+  // as many jobs in flight as three quarters of the free device memory hold: a job is one thread,
+  // so the number of resident counting filters IS the parallelism (12 000 jobs on a 180 GB part)
+  const uint64_t budget = free_b / 4 * 3;
   const uint64_t wave = std::max<uint64_t>(1, std::min<uint64_t>(n_jobs, budget / per_job));
   DevBuf<uint8_t> d_cbf, d_bf;
   GRB_CUDA(c, d_cbf.reserve_exact(wave * p->cbf_bytes, s));
