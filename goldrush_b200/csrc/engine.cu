@@ -1447,7 +1447,14 @@ grb_polish_fill_batches(grb_ctx* c, const grb_polish_params* p, uint32_t n_batch
     w.bf_bytes = p->bf_bytes;
     w.bf_inv = (uint64_t)(((unsigned __int128)1 << 64) / (p->bf_bytes * 8));
     w.status = d_status.p;
-    k_polish_fill<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(w);
+    // GRB_POLISH=thread: one sequential thread per job (the first version, kept as the cross-check);
+    // default: one warp per job, 32 k-mers at a time when their counters are pairwise distinct
+    static const bool per_thread = getenv("GRB_POLISH") && strcmp(getenv("GRB_POLISH"), "thread") == 0;
+    if (per_thread || p->cbf_bytes >= (1ull << 56) || (p->bf_bytes & 3) != 0) {
+      k_polish_fill<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(w);
+    } else {
+      k_polish_fill_warp<<<(unsigned)((n + GRB_PW_WARPS - 1) / GRB_PW_WARPS), 32 * GRB_PW_WARPS, 0, s>>>(w);
+    }
     c->launches += 1;
     GRB_CUDA(c, cudaMemcpyAsync(out_bfs + j0 * p->bf_bytes, d_bf.p, n * p->bf_bytes, cudaMemcpyDeviceToHost, s));
     GRB_CUDA(c, cudaStreamSynchronize(s));

@@ -48,3 +48,148 @@ k_polish_fill(GrbPolishWave w)
     atomicExch(w.status, -1);
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// One WARP per (batch, k) job: 32 consecutive k-mers of a read at a time.
+//
+// The order dependence of the counting filter (polish_core.h) only bites when two k-mers of the
+// group share a counter: if the 32 x hash_num counter indices of a group are pairwise distinct
+// ACROSS lanes, each k-mer's count and update depend on counters nobody else in the group touches,
+// so the 32 updates commute and are applied at once; if any index is shared (identical k-mers in a
+// low-complexity stretch, or a chance collision: 128^2 / 2 / 10^7 = 0.08 % of the groups at the
+// reference's filter size) the group is replayed in lane order.  Groups follow one another in
+// order, reads in order: the result is the sequential one.  Exact detection: the group's indices
+// go into a 256-entry open-addressing table in shared memory, (index, lane) per entry.
+// Bloom-filter bits are ORs and commute; they are set with 32-bit atomics because two lanes may
+// hit one word.
+// ---------------------------------------------------------------------------------------------
+#define GRB_PW_TAB 256 // per-warp conflict table entries (128 indices at hash_num = 4)
+#define GRB_PW_WARPS 4
+
+__device__ __forceinline__ void
+grb_pw_update(const GrbPolishWave& w, uint8_t* cbf, uint32_t* bf32, unsigned h, const uint64_t* at,
+              const uint64_t* idx, unsigned thr, unsigned thr8, uint64_t bf_bits)
+{
+  uint8_t count = 255;
+  for (unsigned q = 0; q < h; ++q) {
+    const uint8_t c = cbf[at[q]];
+    count = c < count ? c : count;
+  }
+  unsigned after = count;
+  if (count < thr8) {
+    for (unsigned q = 0; q < h; ++q) {
+      if (cbf[at[q]] == count) {
+        cbf[at[q]] = (uint8_t)(count + 1);
+      }
+    }
+    after = count + 1u;
+  }
+  if (after >= thr) {
+    for (unsigned q = 0; q < h; ++q) {
+      const uint64_t pos = grb_p_mod(idx[q], bf_bits, w.bf_inv);
+      atomicOr(&bf32[pos >> 5], 1u << (pos & 31)); // little-endian: bit (pos & 7) of byte pos >> 3
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * GRB_PW_WARPS)
+k_polish_fill_warp(GrbPolishWave w)
+{
+  __shared__ unsigned long long s_tab[GRB_PW_WARPS][GRB_PW_TAB];
+  const unsigned lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const uint32_t t = blockIdx.x * GRB_PW_WARPS + wi;
+  if (t >= w.n_jobs) {
+    return;
+  }
+  unsigned long long* tab = s_tab[wi];
+  const uint32_t job = w.job0 + t;
+  const uint32_t batch = job / w.n_k, ki = job - batch * w.n_k;
+  const unsigned k = w.k_values[ki], h = w.hash_num;
+  uint8_t* cbf = w.cbf + (uint64_t)t * w.cbf_bytes;
+  uint32_t* bf32 = reinterpret_cast<uint32_t*>(w.bf + (uint64_t)t * w.bf_bytes);
+  const uint64_t bf_bits = w.bf_bytes * 8;
+  const uint64_t first = w.batch_first[batch], last = w.batch_first[batch + 1];
+  for (uint64_t r = first; r < last; ++r) {
+    const unsigned thr_in = w.thr[r];
+    if (thr_in < 4) {
+      if (lane == 0) {
+        atomicExch(w.status, -1);
+      }
+      return;
+    }
+    const unsigned thr = thr_in - 2 + ki, thr8 = thr > 255 ? 255 : thr;
+    const char* seq = w.seqs + w.off[r];
+    const uint64_t len = w.off[r + 1] - w.off[r];
+    if (len < k) {
+      continue;
+    }
+    const uint64_t n_pos = len - k + 1;
+    for (uint64_t p0 = 0; p0 < n_pos; p0 += 32) {
+      const uint64_t p = p0 + lane;
+      bool valid = p < n_pos;
+      uint64_t fh = 0, rh = 0;
+      if (valid) { // NTF64 / NTR64 from scratch (nthash.hpp:100-119)
+        for (unsigned j = 0; j < k; ++j) {
+          const int cf = grb_p_code((unsigned char)seq[p + j]);
+          const int cr = grb_p_code((unsigned char)seq[p + k - 1 - j]);
+          if (cf < 0) {
+            valid = false;
+            break;
+          }
+          fh = grb_p_srol1(fh) ^ grb_p_seed(cf);
+          rh = grb_p_srol1(rh) ^ grb_p_seed(3 - (cr < 0 ? 0 : cr));
+        }
+      }
+      uint64_t idx[8], at[8];
+      if (valid) {
+        const uint64_t base = fh + rh;
+        idx[0] = base;
+        for (unsigned q = 1; q < h; ++q) {
+          uint64_t x = base * (q ^ k * 0x90b45d39fb6da1faULL);
+          x ^= x >> 27;
+          idx[q] = x;
+        }
+        for (unsigned q = 0; q < h; ++q) {
+          at[q] = grb_p_mod(idx[q], w.cbf_bytes, w.cbf_inv);
+        }
+      }
+      // ---- do two lanes of the group share a counter? ----
+      for (unsigned i = lane; i < GRB_PW_TAB; i += 32) {
+        tab[i] = ~0ull;
+      }
+      __syncwarp();
+      bool conflict = false;
+      if (valid) {
+        for (unsigned q = 0; q < h; ++q) {
+          const unsigned long long mine = ((unsigned long long)at[q] << 8) | lane;
+          unsigned slot = (unsigned)((at[q] * 0x9E3779B97F4A7C15ull) >> 56) & (GRB_PW_TAB - 1);
+          for (unsigned tries = 0; tries < GRB_PW_TAB; ++tries) {
+            const unsigned long long old = atomicCAS(&tab[slot], ~0ull, mine);
+            if (old == ~0ull) {
+              break;
+            }
+            if ((old >> 8) == at[q]) {
+              conflict = conflict || (unsigned)(old & 0xFF) != lane;
+              break;
+            }
+            slot = (slot + 1) & (GRB_PW_TAB - 1);
+          }
+        }
+      }
+      const bool any_conflict = __any_sync(0xffffffffu, conflict) || h * 32 > GRB_PW_TAB / 2;
+      if (!any_conflict) {
+        if (valid) {
+          grb_pw_update(w, cbf, bf32, h, at, idx, thr, thr8, bf_bits);
+        }
+        __syncwarp();
+      } else {
+        for (unsigned l = 0; l < 32; ++l) { // lane order = k-mer order
+          if (l == lane && valid) {
+            grb_pw_update(w, cbf, bf32, h, at, idx, thr, thr8, bf_bits);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+}
