@@ -203,6 +203,7 @@ def lib():
         "grb_polish_plan_target": (i32, [u64, dbl, u32, P(C.c_char_p), vp, vp, vp, P(u32), P(C.c_int32)]),
         "grb_polish_fill_batches": (i32, [vp, P(PolishParams), u32, vp, C.c_char_p, vp, vp, vp]),
         "grb_test_polish_fill_host": (i32, [P(PolishParams), u32, vp, C.c_char_p, vp, vp, vp]),
+        "grb_test_polish_fill_host_grouped": (i32, [P(PolishParams), u32, vp, C.c_char_p, vp, vp, vp, P(u64), P(u64)]),
         "grb_test_plan_silver_parts": (i32, [vp, u32, C.c_int32, vp, vp]),
         "grb_test_decide_host": (i32, [u32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u64, u64, u64,
                                        P(u32), vp, vp, vp]),
@@ -350,10 +351,12 @@ class Engine:
     def reads_count(self):
         return self._L.grb_reads_count(self._h)
 
-    def polish_fill_batches(self, params, batches):
-        """grb_polish_fill_batches: Bloom filters [batch][k index][bf_bytes] of the batches' reads."""
+    def polish_fill_batches(self, params, batches, out=None):
+        """grb_polish_fill_batches: Bloom filters [batch][k index][bf_bytes] of the batches' reads
+        (out: optional preallocated uint8 array, e.g. page-locked with host_pin)."""
         seqs, off, thr, first = _polish_inputs(batches)
-        out = np.zeros(max(1, len(batches) * params.n_k * params.bf_bytes), dtype=np.uint8)
+        if out is None:
+            out = np.zeros(max(1, len(batches) * params.n_k * params.bf_bytes), dtype=np.uint8)
         self._chk(self._L.grb_polish_fill_batches(self._h, C.byref(params), len(batches), _ptr(first), seqs,
                                                   _ptr(off), _ptr(thr), _ptr(out)))
         return out.reshape(len(batches), params.n_k, params.bf_bytes)
@@ -673,6 +676,18 @@ def _polish_inputs(batches):
         first.append(len(thr))
     return (b"".join(seqs), np.array(off, dtype=np.uint64), np.array(thr + [0], dtype=np.uint32),
             np.array(first, dtype=np.uint64))
+
+
+def polish_fill_host_grouped(params, batches):
+    """The warp kernel's algorithm emulated on the host: (filters, groups, groups replayed in lane order)."""
+    seqs, off, thr, first = _polish_inputs(batches)
+    out = np.zeros(max(1, len(batches) * params.n_k * params.bf_bytes), dtype=np.uint8)
+    g, o = C.c_uint64(), C.c_uint64()
+    rc = lib().grb_test_polish_fill_host_grouped(C.byref(params), len(batches), _ptr(first), seqs, _ptr(off),
+                                                 _ptr(thr), _ptr(out), C.byref(g), C.byref(o))
+    if rc:
+        raise GrbError(rc, "grb_test_polish_fill_host_grouped")
+    return out.reshape(len(batches), params.n_k, params.bf_bytes), g.value, o.value
 
 
 def polish_fill_host(params, batches):

@@ -183,39 +183,48 @@ struct GrbPin
 static std::mutex g_pin_mu;
 static std::vector<GrbPin> g_pins;
 
+// host <-> device copy of n bytes whose HOST side is [host, host + n), cut at the piece boundaries
+// of a range page-locked by grb_host_pin
 static cudaError_t
-grb_copy_h2d(void* dst, const char* src, size_t n, cudaStream_t s)
+grb_copy_host(void* dev, const char* host, size_t n, bool to_device, cudaStream_t s)
 {
   GrbPin pin{ nullptr, 0 };
   {
     std::lock_guard<std::mutex> lk(g_pin_mu);
     for (const GrbPin& q : g_pins) {
-      if (src + n > q.base && src < q.base + q.bytes) {
+      if (host + n > q.base && host < q.base + q.bytes) {
         pin = q;
         break;
       }
     }
   }
-  if (!pin.base) {
-    return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s);
-  }
   size_t done = 0;
   while (done < n) {
-    const char* at = src + done;
+    const char* at = host + done;
     size_t len = n - done;
-    if (at < pin.base) {
-      len = std::min<size_t>(len, (size_t)(pin.base - at));
-    } else if (at < pin.base + pin.bytes) {
-      const size_t in_piece = kPinPiece - (size_t)(at - pin.base) % kPinPiece;
-      len = std::min(len, std::min<size_t>(in_piece, (size_t)(pin.base + pin.bytes - at)));
+    if (pin.base) {
+      if (at < pin.base) {
+        len = std::min<size_t>(len, (size_t)(pin.base - at));
+      } else if (at < pin.base + pin.bytes) {
+        const size_t in_piece = kPinPiece - (size_t)(at - pin.base) % kPinPiece;
+        len = std::min(len, std::min<size_t>(in_piece, (size_t)(pin.base + pin.bytes - at)));
+      }
     }
-    const cudaError_t e = cudaMemcpyAsync((char*)dst + done, at, len, cudaMemcpyHostToDevice, s);
+    const cudaError_t e = to_device
+                            ? cudaMemcpyAsync((char*)dev + done, at, len, cudaMemcpyHostToDevice, s)
+                            : cudaMemcpyAsync(const_cast<char*>(at), (const char*)dev + done, len, cudaMemcpyDeviceToHost, s);
     if (e != cudaSuccess) {
       return e;
     }
     done += len;
   }
   return cudaSuccess;
+}
+
+static cudaError_t
+grb_copy_h2d(void* dst, const char* src, size_t n, cudaStream_t s)
+{
+  return grb_copy_host(dst, src, n, true, s);
 }
 
 struct grb_ctx
@@ -1414,6 +1423,21 @@ grb_polish_fill_batches(grb_ctx* c, const grb_polish_params* p, uint32_t n_batch
   GRB_CUDA(c, cudaMemcpyAsync(d_thr.p, thresholds, n_reads * 4, cudaMemcpyHostToDevice, s));
   GRB_CUDA(c, cudaMemcpyAsync(d_k.p, p->k_values, (uint64_t)p->n_k * 4, cudaMemcpyHostToDevice, s));
   GRB_CUDA(c, cudaMemsetAsync(d_status.p, 0, 4, s));
+  // per-k hash tables of the warp kernel (polish_core.h); k above 64 falls back to the thread kernel
+  bool k_too_long = false;
+  for (uint32_t i = 0; i < p->n_k; ++i) {
+    k_too_long = k_too_long || p->k_values[i] > GRB_P_MAX_K || p->k_values[i] == 0;
+  }
+  DevBuf<GrbPolishPair> d_tables;
+  if (!k_too_long) {
+    std::vector<GrbPolishPair> tabs((size_t)p->n_k * GRB_P_GROUPS * 256);
+    for (uint32_t i = 0; i < p->n_k; ++i) {
+      grb_p_build_table(p->k_values[i], tabs.data() + (size_t)i * GRB_P_GROUPS * 256);
+    }
+    GRB_CUDA(c, d_tables.reserve_exact(tabs.size(), s));
+    GRB_CUDA(c, cudaMemcpyAsync(d_tables.p, tabs.data(), tabs.size() * sizeof(GrbPolishPair), cudaMemcpyHostToDevice, s));
+    GRB_CUDA(c, cudaStreamSynchronize(s));
+  }
   size_t free_b = 0, total_b = 0;
   GRB_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   const uint64_t per_job = p->cbf_bytes + p->bf_bytes;
@@ -1450,13 +1474,14 @@ grb_polish_fill_batches(grb_ctx* c, const grb_polish_params* p, uint32_t n_batch
     // GRB_POLISH=thread: one sequential thread per job (the first version, kept as the cross-check);
     // default: one warp per job, 32 k-mers at a time when their counters are pairwise distinct
     static const bool per_thread = getenv("GRB_POLISH") && strcmp(getenv("GRB_POLISH"), "thread") == 0;
-    if (per_thread || p->cbf_bytes >= (1ull << 56) || (p->bf_bytes & 3) != 0) {
+    if (per_thread || k_too_long || p->cbf_bytes >= (1ull << 56) || (p->bf_bytes & 3) != 0) {
       k_polish_fill<<<(unsigned)((n + 31) / 32), 32, 0, s>>>(w);
     } else {
-      k_polish_fill_warp<<<(unsigned)((n + GRB_PW_WARPS - 1) / GRB_PW_WARPS), 32 * GRB_PW_WARPS, 0, s>>>(w);
+      k_polish_fill_warp<<<(unsigned)((n + GRB_PW_WARPS - 1) / GRB_PW_WARPS), 32 * GRB_PW_WARPS, 0, s>>>(
+        w, d_tables.p);
     }
     c->launches += 1;
-    GRB_CUDA(c, cudaMemcpyAsync(out_bfs + j0 * p->bf_bytes, d_bf.p, n * p->bf_bytes, cudaMemcpyDeviceToHost, s));
+    GRB_CUDA(c, grb_copy_host(d_bf.p, (const char*)out_bfs + j0 * p->bf_bytes, n * p->bf_bytes, false, s));
     GRB_CUDA(c, cudaStreamSynchronize(s));
   }
   c->toc();

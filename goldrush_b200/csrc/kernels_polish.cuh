@@ -92,19 +92,30 @@ grb_pw_update(const GrbPolishWave& w, uint8_t* cbf, uint32_t* bf32, unsigned h, 
   }
 }
 
+// A read is handled in segments of GRB_PW_SEG k-mer positions: the warp packs the segment's bases
+// (2 bits each + a mask of the characters outside ACGTacgt) into shared memory once, and every
+// k-mer of the segment is hashed from the packed words through the per-k tables of polish_core.h.
+#define GRB_PW_SEG 1024
+#define GRB_PW_SEG_WORDS ((GRB_PW_SEG + GRB_P_MAX_K) / 32 + 3)
+
 __global__ void __launch_bounds__(32 * GRB_PW_WARPS)
-k_polish_fill_warp(GrbPolishWave w)
+k_polish_fill_warp(GrbPolishWave w, const GrbPolishPair* __restrict__ tables)
 {
   __shared__ unsigned long long s_tab[GRB_PW_WARPS][GRB_PW_TAB];
+  __shared__ uint64_t s_codes[GRB_PW_WARPS][GRB_PW_SEG_WORDS];
+  __shared__ uint32_t s_bad[GRB_PW_WARPS][GRB_PW_SEG_WORDS];
   const unsigned lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const uint32_t t = blockIdx.x * GRB_PW_WARPS + wi;
   if (t >= w.n_jobs) {
     return;
   }
   unsigned long long* tab = s_tab[wi];
+  uint64_t* codes = s_codes[wi];
+  uint32_t* bad = s_bad[wi];
   const uint32_t job = w.job0 + t;
   const uint32_t batch = job / w.n_k, ki = job - batch * w.n_k;
   const unsigned k = w.k_values[ki], h = w.hash_num;
+  const GrbPolishPair* T = tables + (size_t)ki * GRB_P_GROUPS * 256;
   uint8_t* cbf = w.cbf + (uint64_t)t * w.cbf_bytes;
   uint32_t* bf32 = reinterpret_cast<uint32_t*>(w.bf + (uint64_t)t * w.bf_bytes);
   const uint64_t bf_bits = w.bf_bytes * 8;
@@ -124,70 +135,75 @@ k_polish_fill_warp(GrbPolishWave w)
       continue;
     }
     const uint64_t n_pos = len - k + 1;
-    for (uint64_t p0 = 0; p0 < n_pos; p0 += 32) {
-      const uint64_t p = p0 + lane;
-      bool valid = p < n_pos;
-      uint64_t fh = 0, rh = 0;
-      if (valid) { // NTF64 / NTR64 from scratch (nthash.hpp:100-119)
-        for (unsigned j = 0; j < k; ++j) {
-          const int cf = grb_p_code((unsigned char)seq[p + j]);
-          const int cr = grb_p_code((unsigned char)seq[p + k - 1 - j]);
-          if (cf < 0) {
-            valid = false;
-            break;
-          }
-          fh = grb_p_srol1(fh) ^ grb_p_seed(cf);
-          rh = grb_p_srol1(rh) ^ grb_p_seed(3 - (cr < 0 ? 0 : cr));
+    for (uint64_t seg0 = 0; seg0 < n_pos; seg0 += GRB_PW_SEG) {
+      // ---- pack the bases this segment's k-mers cover ----
+      const uint64_t seg_pos = n_pos - seg0 < GRB_PW_SEG ? n_pos - seg0 : GRB_PW_SEG;
+      const uint64_t seg_bases = seg_pos + k - 1;
+      __syncwarp();
+      for (unsigned wd = lane; wd < GRB_PW_SEG_WORDS; wd += 32) {
+        const uint64_t b0 = (uint64_t)wd * 32;
+        uint64_t c = 0;
+        uint32_t m = 0;
+        if (b0 < seg_bases) {
+          const uint64_t n = seg_bases - b0 < 32 ? seg_bases - b0 : 32;
+          grb_p_pack32(seq + seg0 + b0, (unsigned)n, &c, &m);
         }
-      }
-      uint64_t idx[8], at[8];
-      if (valid) {
-        const uint64_t base = fh + rh;
-        idx[0] = base;
-        for (unsigned q = 1; q < h; ++q) {
-          uint64_t x = base * (q ^ k * 0x90b45d39fb6da1faULL);
-          x ^= x >> 27;
-          idx[q] = x;
-        }
-        for (unsigned q = 0; q < h; ++q) {
-          at[q] = grb_p_mod(idx[q], w.cbf_bytes, w.cbf_inv);
-        }
-      }
-      // ---- do two lanes of the group share a counter? ----
-      for (unsigned i = lane; i < GRB_PW_TAB; i += 32) {
-        tab[i] = ~0ull;
+        codes[wd] = c;
+        bad[wd] = m;
       }
       __syncwarp();
-      bool conflict = false;
-      if (valid) {
-        for (unsigned q = 0; q < h; ++q) {
-          const unsigned long long mine = ((unsigned long long)at[q] << 8) | lane;
-          unsigned slot = (unsigned)((at[q] * 0x9E3779B97F4A7C15ull) >> 56) & (GRB_PW_TAB - 1);
-          for (unsigned tries = 0; tries < GRB_PW_TAB; ++tries) {
-            const unsigned long long old = atomicCAS(&tab[slot], ~0ull, mine);
-            if (old == ~0ull) {
-              break;
-            }
-            if ((old >> 8) == at[q]) {
-              conflict = conflict || (unsigned)(old & 0xFF) != lane;
-              break;
-            }
-            slot = (slot + 1) & (GRB_PW_TAB - 1);
+      for (uint64_t g0 = 0; g0 < seg_pos; g0 += 32) {
+        const uint64_t q = g0 + lane;
+        uint64_t base = 0;
+        const bool valid = q < seg_pos && grb_p_hash_packed(codes, bad, (unsigned)q, k, T, &base);
+        uint64_t idx[8], at[8];
+        if (valid) {
+          idx[0] = base;
+          for (unsigned u = 1; u < h; ++u) {
+            uint64_t x = base * (u ^ k * 0x90b45d39fb6da1faULL);
+            x ^= x >> 27;
+            idx[u] = x;
+          }
+          for (unsigned u = 0; u < h; ++u) {
+            at[u] = grb_p_mod(idx[u], w.cbf_bytes, w.cbf_inv);
           }
         }
-      }
-      const bool any_conflict = __any_sync(0xffffffffu, conflict) || h * 32 > GRB_PW_TAB / 2;
-      if (!any_conflict) {
-        if (valid) {
-          grb_pw_update(w, cbf, bf32, h, at, idx, thr, thr8, bf_bits);
+        // ---- do two lanes of the group share a counter? ----
+        for (unsigned i = lane; i < GRB_PW_TAB; i += 32) {
+          tab[i] = ~0ull;
         }
         __syncwarp();
-      } else {
-        for (unsigned l = 0; l < 32; ++l) { // lane order = k-mer order
-          if (l == lane && valid) {
+        bool conflict = false;
+        if (valid) {
+          for (unsigned u = 0; u < h; ++u) {
+            const unsigned long long mine = ((unsigned long long)at[u] << 8) | lane;
+            unsigned slot = (unsigned)((at[u] * 0x9E3779B97F4A7C15ull) >> 56) & (GRB_PW_TAB - 1);
+            for (unsigned tries = 0; tries < GRB_PW_TAB; ++tries) {
+              const unsigned long long old = atomicCAS(&tab[slot], ~0ull, mine);
+              if (old == ~0ull) {
+                break;
+              }
+              if ((old >> 8) == at[u]) {
+                conflict = conflict || (unsigned)(old & 0xFF) != lane;
+                break;
+              }
+              slot = (slot + 1) & (GRB_PW_TAB - 1);
+            }
+          }
+        }
+        const bool any_conflict = __any_sync(0xffffffffu, conflict) || h * 32 > GRB_PW_TAB / 2;
+        if (!any_conflict) {
+          if (valid) {
             grb_pw_update(w, cbf, bf32, h, at, idx, thr, thr8, bf_bits);
           }
           __syncwarp();
+        } else {
+          for (unsigned l = 0; l < 32; ++l) { // lane order = k-mer order
+            if (l == lane && valid) {
+              grb_pw_update(w, cbf, bf32, h, at, idx, thr, thr8, bf_bits);
+            }
+            __syncwarp();
+          }
         }
       }
     }

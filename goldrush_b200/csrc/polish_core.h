@@ -172,3 +172,92 @@ grb_polish_run(const GrbPolishJob& j)
   }
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Table-driven hashing for the warp kernel (kernels_polish.cuh): the read is 2-bit packed (32 bases
+// per 64-bit word, base i of a word at bits 2i, 2i + 1; a parallel mask word holds the characters
+// outside ACGTacgt), a k-mer's 2k bits are cut out of the packed words, and its forward / reverse
+// hashes are XORs of one table entry per group of 4 bases:
+//   T[g][v].x = XOR over i < 4, 4g + i < k of srol^(k - 1 - (4g + i))(seed[b_i])        (NTF64)
+//   T[g][v].y = XOR over i < 4, 4g + i < k of srol^(4g + i)(seed[3 - b_i])              (NTR64)
+// with b_i = (v >> 2i) & 3: ceil(k / 4) lookups instead of k rotate-and-xor steps per strand.
+// ---------------------------------------------------------------------------------------------
+#define GRB_P_MAX_K 64
+#define GRB_P_GROUPS (GRB_P_MAX_K / 4)
+
+struct GrbPolishPair
+{
+  uint64_t x, y;
+};
+
+// host: the table of one k, GRB_P_GROUPS * 256 entries (groups beyond ceil(k / 4) are zero)
+inline void
+grb_p_build_table(unsigned k, GrbPolishPair* T)
+{
+  for (unsigned g = 0; g < GRB_P_GROUPS; ++g) {
+    for (unsigned v = 0; v < 256; ++v) {
+      uint64_t f = 0, r = 0;
+      for (unsigned i = 0; i < 4; ++i) {
+        const unsigned pos = 4 * g + i;
+        if (pos < k) {
+          const int b = (int)((v >> (2 * i)) & 3u);
+          f ^= grb_p_srol(grb_p_seed(b), k - 1 - pos);
+          r ^= grb_p_srol(grb_p_seed(3 - b), pos);
+        }
+      }
+      T[g * 256 + v] = GrbPolishPair{ f, r };
+    }
+  }
+}
+
+// 32 characters -> packed codes + mask of the characters outside ACGTacgt (n < 32 at the read's end)
+GRB_PHD void
+grb_p_pack32(const char* s, unsigned n, uint64_t* codes, uint32_t* bad)
+{
+  uint64_t c = 0;
+  uint32_t m = 0;
+  for (unsigned i = 0; i < n; ++i) {
+    const int b = grb_p_code((unsigned char)s[i]);
+    c |= (uint64_t)(b < 0 ? 0 : b) << (2 * i);
+    m |= (b < 0 ? 1u : 0u) << i;
+  }
+  *codes = c;
+  *bad = m;
+}
+
+// k-mer starting at local position q of a packed segment: false if it holds a bad character, else
+// its canonical hash (fh + rh)
+GRB_PHD bool
+grb_p_hash_packed(const uint64_t* codes, const uint32_t* bad, unsigned q, unsigned k, const GrbPolishPair* T,
+                  uint64_t* base)
+{
+  const unsigned w = q >> 5, o = q & 31;
+  // k mask bits from bit o of bad[w..w+2]
+  const uint64_t m01 = (uint64_t)bad[w] | ((uint64_t)bad[w + 1] << 32);
+  uint64_t mk = m01 >> o;
+  if (o) {
+    mk |= (uint64_t)bad[w + 2] << (64 - o);
+  }
+  if (k < 64) {
+    mk &= (1ull << k) - 1ull;
+  }
+  if (mk) {
+    return false;
+  }
+  // 2k code bits from bit 2o of codes[w..w+2]
+  uint64_t lo = codes[w] >> (2 * o), hi = codes[w + 1] >> (2 * o);
+  if (o) {
+    lo |= codes[w + 1] << (64 - 2 * o);
+    hi |= codes[w + 2] << (64 - 2 * o);
+  }
+  uint64_t fh = 0, rh = 0;
+  const unsigned groups = (k + 3) / 4;
+  for (unsigned g = 0; g < groups; ++g) {
+    const unsigned v = (unsigned)((g < 8 ? lo >> (8 * g) : hi >> (8 * (g - 8))) & 0xFFu);
+    const GrbPolishPair t = T[g * 256 + v];
+    fh ^= t.x;
+    rh ^= t.y;
+  }
+  *base = fh + rh;
+  return true;
+}

@@ -449,6 +449,13 @@ int grb_polish_fill_batches(grb_ctx* ctx, const grb_polish_params* p, uint32_t n
 int grb_test_polish_fill_host(const grb_polish_params* p, uint32_t n_batches, const uint64_t* batch_first,
                               const char* seqs, const uint64_t* seq_off, const uint32_t* thresholds,
                               uint8_t* out_bfs);
+/* test hook: the warp kernel's algorithm lane by lane on the host (packed segments, table-driven
+ * hashing, groups of 32 k-mers applied at once when no counter is shared between two lanes, in lane
+ * order otherwise); also reports how many groups there were and how many needed lane order. */
+int grb_test_polish_fill_host_grouped(const grb_polish_params* p, uint32_t n_batches,
+                                      const uint64_t* batch_first, const char* seqs, const uint64_t* seq_off,
+                                      const uint32_t* thresholds, uint8_t* out_bfs, uint64_t* groups_total,
+                                      uint64_t* groups_in_lane_order);
 
 /* ---- synthetic reads; host only, used by bench.py and the tests ---- */
 typedef struct grb_synth_params

@@ -81,9 +81,33 @@ CASES = {
     "small_filters_collide": (11, 3, 25, [32, 28, 24], 4, 1 << 15, 1 << 14),
     "reference_sizes": (12, 2, 120, [40, 32, 24], 4, 10 << 20, 512 << 10),
     "two_hashes_one_k": (13, 4, 12, [20], 2, 1 << 16, 1 << 12),
+    # homopolymers and short tandem repeats: identical k-mers side by side, i.e. groups of 32 k-mers
+    # that share counters and must be applied in order; k up to the table limit of 64
+    "low_complexity": (14, 3, 20, [64, 33, 17], 4, 1 << 16, 1 << 13),
 }
+
+
+def add_repeats(batches, seed):
+    rnd = random.Random(seed)
+    out = []
+    for batch in batches:
+        nb = []
+        for s, t in batch:
+            s = bytearray(s)
+            for _ in range(3):
+                if len(s) > 400:
+                    at = rnd.randint(0, len(s) - 300)
+                    unit = bytes(rnd.choice(b"ACGT") for _ in range(rnd.choice([1, 1, 2, 3, 7])))
+                    n = rnd.randint(60, 250)
+                    s[at:at + n] = (unit * n)[:n]
+            nb.append((bytes(s), t))
+        out.append(nb)
+    return out
 
 
 def case_batches(name):
     seed, nb, rpb, ks, h, cbf, bf = CASES[name]
-    return make_batches(seed, nb, rpb), ks, h, cbf, bf
+    batches = make_batches(seed, nb, rpb)
+    if name == "low_complexity":
+        batches = add_repeats(batches, seed)
+    return batches, ks, h, cbf, bf

@@ -82,6 +82,21 @@ def test_job_code_on_the_host_matches_the_port(name):
     assert hashlib.md5(got.tobytes()).hexdigest() == GOLDEN[name]["md5"]
 
 
+@pytest.mark.parametrize("name", sorted(pu.CASES))
+def test_warp_algorithm_on_the_host_matches_the_port(name):
+    """The warp kernel's algorithm emulated lane by lane (2-bit packed segments, table-driven hashes,
+    32 k-mers applied at once -- all counts read before any write -- unless two lanes share a
+    counter): the same filters as the sequential port, i.e. conflict-free groups do commute."""
+    batches, ks, h, cbf, bf = pu.case_batches(name)
+    got, groups, ordered = grb.api.polish_fill_host_grouped(grb.api.polish_params(ks, h, cbf, bf), batches)
+    assert hashlib.md5(got.tobytes()).hexdigest() == GOLDEN[name]["md5"]
+    assert groups > 0
+    if name == "low_complexity":
+        assert ordered > 50  # repeats put identical k-mers into one group
+    if name == "reference_sizes":
+        assert ordered < groups // 50  # chance collisions are rare at 10 MiB
+
+
 def test_threshold_below_four_is_refused():
     p = grb.api.polish_params([24], 4, 1 << 12, 1 << 10)
     with pytest.raises(grb.GrbError):
