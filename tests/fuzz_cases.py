@@ -1,0 +1,38 @@
+"""Seeded parameter fuzz over the goldrush-path option space (k, weight, h, tile, block, smoothing
+and Phred options, silver / golden mode, fixed and log-normal read lengths).  The same case list is
+run three ways: reference sources == oracle port on CPU (test_oracle_vs_ref.py) and drop-in
+executable == oracle on the GPU (test_gpu_parity.py).  Nothing here is a committed expectation:
+both sides are computed at test time from the seeded input."""
+import numpy as np
+
+import parity_util as pu
+
+N_CASES = 16
+
+
+def _case(i):
+    rng = np.random.default_rng(7000 + i)
+    k = int(rng.choice([16, 18, 20, 22, 24, 26, 28, 32]))
+    half = int(rng.integers(max(3, k // 4), k // 2))  # ones per half, below k/2 so the design loop ends fast
+    h = int(rng.integers(1, 5))
+    t = int(rng.choice([200, 300, 500, 1000]))
+    G = int(rng.integers(80, 250)) * 1000
+    cov = int(rng.integers(8, 15))
+    lognormal = bool(rng.random() < 0.35)
+    L = 0 if lognormal else int(rng.integers(12, 40)) * t // 2
+    n50 = int(rng.integers(10, 30)) * t // 2
+    silver = bool(rng.random() < 0.7)
+    m = int((n50 if lognormal else L) * rng.choice([0.5, 0.8, 1.0])) if silver else 0
+    args = ["-k", str(k), "-w", str(2 * half), "-h", str(h), "-t", str(t),
+            "-b", str(int(rng.integers(2, 11))), "-u", str(int(rng.integers(3, 7))),
+            "-a", str(int(rng.integers(1, 3))), "-o", str(rng.choice([0.05, 0.1, 0.2])),
+            "-x", str(int(rng.integers(5, 13))), "-d", str(int(rng.integers(3, 9))),
+            "-P", str(int(rng.choice([0, 12, 15, 18]))), "-g", str(G), "-m", str(m), "--verbose"]
+    if silver:
+        args += ["-r", str(rng.choice([0.7, 0.8, 0.9])), "-M", str(int(rng.choice([1, 2, 3, 5]))),
+                 "--silver_path"]
+    return dict(name=f"fuzz{i:02d}", synth=pu.golden_cases.synth_args(G, cov, L, 7100 + i, n50=n50),
+                args=args)
+
+
+CASES = [_case(i) for i in range(N_CASES)]

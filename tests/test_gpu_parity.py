@@ -6,6 +6,7 @@ import os
 import numpy as np
 import pytest
 
+import fuzz_cases
 import goldrush_b200 as grb
 import oracle_util as ou
 import parity_util as pu
@@ -336,6 +337,21 @@ def test_cli_binary_matches_reference_fixture(name, workdir):
     assert rc == g["exit_code"], err[-2000:]
     assert pu.digest_outputs(outs) == g["outputs"]
     assert pu.parse_stats(err) == g["stats"]
+
+
+@pytest.mark.parametrize("case", fuzz_cases.CASES, ids=[c["name"] for c in fuzz_cases.CASES])
+def test_parameter_fuzz_cli_equals_oracle(case, workdir):
+    """Seeded fuzz over the option space (tests/fuzz_cases.py: k 16-32, any weight, h 1-4, tile
+    200-1000, block / smoothing / Phred options, silver and golden mode, fixed and log-normal
+    lengths): the drop-in executable against the CPU oracle run here on the same input — files by
+    md5, exit code, --verbose counters.  The CPU suite checks the oracle against the reference's
+    own sources on this very list."""
+    inp, extra = pu.make_input(case, workdir)
+    rc_o, outs_o, err_o = pu.run_cli(pu.ORACLE, case, inp, extra, workdir, "ora", jobs=4)
+    rc_g, outs_g, err_g = pu.run_cli(pu.PRODUCT, case, inp, extra, workdir, "gpu", jobs=4)
+    assert rc_g == rc_o == 0, err_g[-2000:]
+    assert outs_o and pu.digest_outputs(outs_g) == pu.digest_outputs(outs_o)
+    assert pu.parse_stats(err_g) == pu.parse_stats(err_o)
 
 
 @pytest.mark.parametrize("pair", [("silver_default", "golden_default"), ("silver_m12", "golden_m12")])

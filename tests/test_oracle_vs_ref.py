@@ -7,6 +7,7 @@ import os
 
 import pytest
 
+import fuzz_cases
 import parity_util as pu
 
 pytestmark = pytest.mark.skipif(not os.path.exists(pu.REF), reason="oracle/_ref not built here")
@@ -34,6 +35,20 @@ def test_oracle_equals_reference_binary(case, workdir):
     rc_o, outs_o, err_o = pu.run_cli(pu.ORACLE, case, inp, extra, workdir, "ora", jobs=4)
     assert rc_r == rc_o, (err_r[-400:], err_o[-400:])
     assert outs_r, "reference wrote nothing: " + err_r[-400:]
+    assert pu.digest_outputs(outs_r) == pu.digest_outputs(outs_o)
+    assert pu.parse_stats(err_r) == pu.parse_stats(err_o)
+
+
+@pytest.mark.parametrize("case", fuzz_cases.CASES, ids=[c["name"] for c in fuzz_cases.CASES])
+def test_parameter_fuzz_oracle_equals_reference_binary(case, workdir):
+    """Seeded fuzz over k / weight / h / tile / smoothing / Phred options and both modes
+    (tests/fuzz_cases.py): files, exit code and --verbose counters of the port equal the reference
+    sources'.  The GPU suite runs the drop-in executable over the same list."""
+    inp, extra = pu.make_input(case, workdir)
+    rc_r, outs_r, err_r = pu.run_cli(pu.REF, case, inp, extra, workdir, "ref", jobs=2)
+    rc_o, outs_o, err_o = pu.run_cli(pu.ORACLE, case, inp, extra, workdir, "ora", jobs=4)
+    assert rc_r == rc_o == 0, (err_r[-400:], err_o[-400:])
+    assert outs_r and sum(d["bytes"] for d in pu.digest_outputs(outs_r)) > 0
     assert pu.digest_outputs(outs_r) == pu.digest_outputs(outs_o)
     assert pu.parse_stats(err_r) == pu.parse_stats(err_o)
 
