@@ -17,7 +17,7 @@ LIBDIR := $(ROOT)goldrush_b200/_lib
 LIB    := $(LIBDIR)/libgoldrush_b200.so
 CU_SRC := $(wildcard $(ROOT)goldrush_b200/csrc/*.cu)
 CU_HDR := $(wildcard $(ROOT)goldrush_b200/csrc/*.cuh) $(wildcard $(ROOT)goldrush_b200/csrc/*.h) $(ROOT)include/goldrush_b200.h
-HOST_LIB_SRC := $(ROOT)goldrush_b200/host/synth.cpp $(ROOT)goldrush_b200/host/host_util.cpp $(ROOT)goldrush_b200/host/path_driver.cpp $(ROOT)goldrush_b200/host/decide_host.cpp $(ROOT)goldrush_b200/host/polish_driver.cpp
+HOST_LIB_SRC := $(ROOT)goldrush_b200/host/synth.cpp $(ROOT)goldrush_b200/host/host_util.cpp $(ROOT)goldrush_b200/host/path_driver.cpp $(ROOT)goldrush_b200/host/decide_host.cpp $(ROOT)goldrush_b200/host/polish_driver.cpp $(ROOT)goldrush_b200/host/polish_inputs.cpp
 
 all: lib goldrush-path host-tools
 

@@ -204,6 +204,13 @@ def lib():
         "grb_polish_fill_batches": (i32, [vp, P(PolishParams), u32, vp, C.c_char_p, vp, vp, vp]),
         "grb_test_polish_fill_host": (i32, [P(PolishParams), u32, vp, C.c_char_p, vp, vp, vp]),
         "grb_test_polish_fill_host_grouped": (i32, [P(PolishParams), u32, vp, C.c_char_p, vp, vp, vp, P(u64), P(u64)]),
+        "grb_polish_index_build": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, sz]),
+        "grb_polish_inputs_open": (i32, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, dbl, P(vp), C.c_char_p, sz]),
+        "grb_polish_inputs_close": (None, [vp]),
+        "grb_polish_inputs_mappings": (C.c_int64, [vp, C.c_char_p, C.c_char_p, sz]),
+        "grb_polish_serve_batches": (i32, [vp, vp, P(PolishParams), dbl, u32, vp, P(C.c_char_p), vp, C.c_char_p, sz]),
+        "grb_test_polish_serve_batches_host": (i32, [vp, P(PolishParams), dbl, u32, vp, P(C.c_char_p), vp, P(u64),
+                                                     P(u64), C.c_char_p, sz]),
         "grb_test_plan_silver_parts": (i32, [vp, u32, C.c_int32, vp, vp]),
         "grb_test_decide_host": (i32, [u32, vp, vp, vp, vp, vp, u32, u64, u64, u64, u64, u64, u64,
                                        P(u32), vp, vp, vp]),
@@ -359,6 +366,18 @@ class Engine:
             out = np.zeros(max(1, len(batches) * params.n_k * params.bf_bytes), dtype=np.uint8)
         self._chk(self._L.grb_polish_fill_batches(self._h, C.byref(params), len(batches), _ptr(first), seqs,
                                                   _ptr(off), _ptr(thr), _ptr(out)))
+        return out.reshape(len(batches), params.n_k, params.bf_bytes)
+
+    def polish_serve_batches(self, inputs, params, subsample_max_per_10kbp, batches, out=None):
+        """grb_polish_serve_batches: batches = lists of target ids; Bloom filters [batch][k index][bf_bytes]."""
+        first, ids = _polish_target_lists(batches)
+        if out is None:
+            out = np.zeros(max(1, len(batches) * params.n_k * params.bf_bytes), dtype=np.uint8)
+        err = C.create_string_buffer(1024)
+        rc = self._L.grb_polish_serve_batches(self._h, inputs._h, C.byref(params), float(subsample_max_per_10kbp),
+                                              len(batches), _ptr(first), ids, _ptr(out), err, len(err))
+        if rc:
+            raise GrbError(rc, err.value.decode(errors="replace"))
         return out.reshape(len(batches), params.n_k, params.bf_bytes)
 
     def reads_set_origin(self, byte_offset):
@@ -698,6 +717,69 @@ def polish_fill_host(params, batches):
     if rc:
         raise GrbError(rc, "grb_test_polish_fill_host")
     return out.reshape(len(batches), params.n_k, params.bf_bytes)
+
+
+def polish_index_build(seqs_path, index_path):
+    """grb_polish_index_build: what goldpolish-index writes for a FASTA / FASTQ file."""
+    err = C.create_string_buffer(1024)
+    rc = lib().grb_polish_index_build(os.fsencode(seqs_path), os.fsencode(index_path), err, len(err))
+    if rc:
+        raise GrbError(rc, err.value.decode(errors="replace"))
+
+
+def _polish_target_lists(batches):
+    first = np.zeros(len(batches) + 1, dtype=np.uint64)
+    flat = []
+    for i, b in enumerate(batches):
+        flat += [t.encode() if isinstance(t, str) else t for t in b]
+        first[i + 1] = len(flat)
+    return first, (C.c_char_p * max(1, len(flat)))(*flat)
+
+
+class PolishInputs:
+    """grb_polish_inputs: the two sequence indexes and the mappings goldpolish-targeted-bfs loads."""
+
+    def __init__(self, target_index, mappings, mapped_seqs, mapped_index, mx_max_per_10kbp):
+        h = C.c_void_p()
+        err = C.create_string_buffer(1024)
+        rc = lib().grb_polish_inputs_open(os.fsencode(target_index), os.fsencode(mappings), os.fsencode(mapped_seqs),
+                                          os.fsencode(mapped_index), float(mx_max_per_10kbp), C.byref(h), err,
+                                          len(err))
+        if rc:
+            raise GrbError(rc, err.value.decode(errors="replace"))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib().grb_polish_inputs_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def mappings(self, target_id):
+        """AllMappings::get_mappings: ids of the reads kept for the target, in load order."""
+        buf = C.create_string_buffer(1 << 20)
+        n = lib().grb_polish_inputs_mappings(self._h, target_id.encode(), buf, len(buf))
+        ids = buf.value.decode().split("\n")[:-1]
+        assert len(ids) == n, (len(ids), n)
+        return ids
+
+    def serve_batches_host(self, params, subsample_max_per_10kbp, batches):
+        """Test hook: (filters, reads inserted, bases inserted) with the job code run on the host."""
+        first, ids = _polish_target_lists(batches)
+        out = np.zeros(max(1, len(batches) * params.n_k * params.bf_bytes), dtype=np.uint8)
+        nr, nb = C.c_uint64(), C.c_uint64()
+        err = C.create_string_buffer(1024)
+        rc = lib().grb_test_polish_serve_batches_host(self._h, C.byref(params), float(subsample_max_per_10kbp),
+                                                      len(batches), _ptr(first), ids, _ptr(out), C.byref(nr),
+                                                      C.byref(nb), err, len(err))
+        if rc:
+            raise GrbError(rc, err.value.decode(errors="replace"))
+        return out.reshape(len(batches), params.n_k, params.bf_bytes), nr.value, nb.value
 
 
 def host_pin(ptr, nbytes):

@@ -457,6 +457,47 @@ int grb_test_polish_fill_host_grouped(const grb_polish_params* p, uint32_t n_bat
                                       const uint32_t* thresholds, uint8_t* out_bfs, uint64_t* groups_total,
                                       uint64_t* groups_in_lane_order);
 
+/* ---- (f4) the builder's inputs: sequence indexes and mappings (host only) ---- */
+/* goldpolish-index (subprojects/goldpolish/src/goldpolish_index.cpp:13-14; SeqIndex::SeqIndex(seqs)
+ * seqindex.cpp:12-66 and save :68-84): one line `id \t seq_start \t seq_len \t phred_avg` per record of
+ * a FASTQ (4-line records) or FASTA (2-line records) file, phred_avg printed as the reference's stream
+ * does (%g).  Lines come in file order (the reference: in the order of its hash table); a repeated id
+ * keeps its first record. */
+int grb_polish_index_build(const char* seqs_path, const char* index_path, char* err, size_t err_cap);
+/* What goldpolish-targeted-bfs loads before it serves batches (goldpolish_targeted_bfs.cpp:271-281):
+ * the index of the target sequences and of the mapped sequences (seqindex.cpp:86-123) and the
+ * mappings -- SAM (columns 1, 3) for `.sam`, PAF (columns 1, 6) for `.paf`, otherwise ntLink's
+ * `read target minimizers` triples, filtered per target to at most ceil(len * mx_max / 10000) reads
+ * by raising the minimizer threshold within [1, 30] (mappings.cpp:12-31,71-107,226-320).  Mappings to
+ * targets outside the index are dropped, a read counts once per target.  `.bam` is refused (the
+ * reference pipes it through samtools). */
+typedef struct grb_polish_inputs grb_polish_inputs;
+int grb_polish_inputs_open(const char* target_index_path, const char* mappings_path,
+                           const char* mapped_seqs_path, const char* mapped_index_path,
+                           double mx_max_mapped_seqs_per_target_10kbp, grb_polish_inputs** out, char* err,
+                           size_t err_cap);
+void grb_polish_inputs_close(grb_polish_inputs* in);
+/* AllMappings::get_mappings (mappings.cpp:322-329): how many reads are kept for the target; their ids,
+ * each followed by '\n', into buf as far as cap allows (buf may be NULL). */
+int64_t grb_polish_inputs_mappings(const grb_polish_inputs* in, const char* target_id, char* buf, size_t cap);
+/* serve_batch (goldpolish_targeted_bfs.cpp:84-136) for n_batches batches in one call: batch b = the
+ * target ids target_ids[batch_first[b] .. batch_first[b + 1]) in the order the caller would write them
+ * to the batch's pipe.  Per target: grb_polish_plan_target over its mapped reads, the chosen reads
+ * fetched from the mapped-sequence file (SeqIndex::get_seq, seqindex.hpp:64-103), then
+ * grb_polish_fill_batches; out_bfs as there.  A target id missing from the target index, or a mapped
+ * read missing from the mapped-sequence index, is an error (the reference: uncaught std::out_of_range). */
+int grb_polish_serve_batches(grb_ctx* ctx, const grb_polish_inputs* in, const grb_polish_params* p,
+                             double subsample_max_mapped_seqs_per_target_10kbp, uint32_t n_batches,
+                             const uint64_t* batch_first, const char* const* target_ids, uint8_t* out_bfs,
+                             char* err, size_t err_cap);
+/* test hook: the same gathering, then the host-compiled job code instead of the GPU; also reports how
+ * many reads and bases the batches hold.  Never called by the product path. */
+int grb_test_polish_serve_batches_host(const grb_polish_inputs* in, const grb_polish_params* p,
+                                       double subsample_max_mapped_seqs_per_target_10kbp, uint32_t n_batches,
+                                       const uint64_t* batch_first, const char* const* target_ids,
+                                       uint8_t* out_bfs, uint64_t* n_reads, uint64_t* n_bases, char* err,
+                                       size_t err_cap);
+
 /* ---- synthetic reads; host only, used by bench.py and the tests ---- */
 typedef struct grb_synth_params
 {

@@ -16,6 +16,13 @@ check_error(bool condition, const std::string& msg)
   }
 }
 inline void log_info(const std::string& msg) { std::cerr << "[INFO] " << msg << std::endl; }
+inline void log_error(const std::string& msg) { std::cerr << "[ERROR] " << msg << std::endl; }
 inline std::string get_strerror() { return std::strerror(errno); }
+template<class Stream>
+inline void
+check_stream(const Stream& stream, const std::string& name)
+{
+  check_error(!stream.good(), "'" + name + "' stream error: " + get_strerror());
+}
 } // namespace btllib
 #endif

@@ -1,0 +1,162 @@
+"""(f4) the input side of the GoldPolish targeted-Bloom-filter builder: sequence index, mappings
+(ntLink / PAF / SAM), and serve_batch's per-target planning and sequence fetch, against the
+reference's own SeqIndex / AllMappings / serve_batch (oracle/_ref/libgoldpolish_ref.so, compiled
+unmodified) and against the fixtures it wrote (tests/golden/polish_inputs.json).  The CPU tests run
+the host side with the job code compiled for the host; the GPU tests run the same call with the
+kernels."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import goldrush_b200 as grb
+import polish_inputs_util as piu
+import polish_util as pu
+
+with open(os.path.join(pu.ROOT, "tests", "golden", "polish_inputs.json")) as f:
+    GOLDEN = json.load(f)
+HAVE_REF = os.path.exists(pu.REF_SO)
+NAMES = sorted(piu.SCENARIOS)
+
+
+def _prepared(name, workdir):
+    sc = piu.make_files(name, str(workdir))
+    ti, ri = os.path.join(sc["dir"], "targets.idx"), os.path.join(sc["dir"], "reads.idx")
+    grb.api.polish_index_build(sc["targets"], ti)
+    grb.api.polish_index_build(sc["reads"], ri)
+    return sc, ti, ri
+
+
+def _open(sc, ti, ri):
+    return grb.api.PolishInputs(ti, sc["mappings"], sc["reads"], ri, sc["mx_max"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_index_files_hold_the_lines_the_reference_writes(name, workdir):
+    """goldpolish-index: same lines (the reference writes them in hash-table order, so as a set):
+    FASTA and FASTQ, ids cut at the first blank / tab, a repeated id keeps its first record,
+    Phred average over all but the last quality character, %g formatting."""
+    sc, ti, ri = _prepared(name, workdir)
+    assert list(piu.sorted_lines_md5(ti)) == GOLDEN[name]["target_index"]
+    assert list(piu.sorted_lines_md5(ri)) == GOLDEN[name]["mapped_index"]
+    if HAVE_REF:
+        for seqs, mine in ((sc["targets"], ti), (sc["reads"], ri)):
+            piu.ref_index(seqs, mine + ".ref")
+            assert piu.sorted_lines_md5(mine + ".ref") == piu.sorted_lines_md5(mine)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_kept_mappings_equal_the_references(name, workdir):
+    """AllMappings after loading (+ the minimizer filter for ntLink input): per target the same read
+    ids in the same order; targets outside the index and unknown ids give nothing."""
+    sc, ti, ri = _prepared(name, workdir)
+    with _open(sc, ti, ri) as pin:
+        for t, want in GOLDEN[name]["mappings"].items():
+            assert pin.mappings(t) == want, t
+        assert pin.mappings("never_seen") == []
+        if HAVE_REF:
+            for t in sc["target_ids"]:
+                assert pin.mappings(t) == piu.ref_mappings(sc, ti, t)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_serve_batches_on_the_host_equals_the_references_serve_batch(name, workdir):
+    sc, ti, ri = _prepared(name, workdir)
+    params = grb.api.polish_params(sc["ks"], 4, sc["cbf"], sc["bf"])
+    with _open(sc, ti, ri) as pin:
+        got, n_reads, n_bases = pin.serve_batches_host(params, sc["subsample"], sc["batches"])
+    g = GOLDEN[name]
+    assert np.unpackbits(got, axis=2).sum(axis=2).tolist() == g["set_bits"]
+    assert hashlib.md5(got.tobytes()).hexdigest() == g["bfs_md5"]
+    assert n_reads > 0 and n_bases > n_reads
+    if HAVE_REF:
+        assert (got == piu.ref_serve(sc, ti, ri)).all()
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built here")
+@pytest.mark.parametrize("seed", range(8))
+def test_minimizer_filter_fuzz_against_the_reference(seed, workdir):
+    """AllMappings::filter (mappings.cpp:226-320) on hand-written index files: targets short and long,
+    few and many mappings, minimizer counts clustered so that all three branches (everything fits /
+    too many even at the top threshold / bisection) are taken."""
+    rnd = random.Random(900 + seed)
+    d = os.path.join(str(workdir), f"filter{seed}")
+    os.makedirs(d, exist_ok=True)
+    tidx, midx, mp = (os.path.join(d, n) for n in ("t.idx", "m.idx", "map.tsv"))
+    seqs = os.path.join(d, "none.fq")
+    open(seqs, "w").close()
+    open(midx, "w").close()
+    targets = [(f"c{i}", rnd.choice([400, 3000, 12000, 60000, 250000])) for i in range(12)]
+    with open(tidx, "w") as f:
+        for t, ln in targets:
+            f.write(f"{t}\t{rnd.randint(0, 10**6)}\t{ln}\t0\n")
+    with open(mp, "w") as f:
+        rows = []
+        for t, ln in targets:
+            style = rnd.choice(["low", "high", "spread"])
+            for j in range(rnd.choice([1, 4, 30, 120])):
+                mx = {"low": rnd.randint(0, 6), "high": rnd.randint(28, 45), "spread": rnd.randint(0, 45)}[style]
+                rows.append(f"q{j}_{t} {t} {mx}\n")
+        rnd.shuffle(rows)
+        f.writelines(rows)
+    mx_max = rnd.choice([0.5, 3.0, 10.0, 40.0])
+    sc = dict(targets=seqs, mappings=mp, mx_max=mx_max)
+    kept = 0
+    with grb.api.PolishInputs(tidx, mp, seqs, midx, mx_max) as pin:
+        for t, _ in targets:
+            mine = pin.mappings(t)
+            assert mine == piu.ref_mappings(sc, tidx, t), (t, mx_max)
+            kept += len(mine)
+    assert kept > 0
+
+
+def test_input_errors_are_reported_not_fatal(workdir):
+    """Where the reference dies (uncaught std::out_of_range from .at(), exit(1) from check_error), the
+    library returns an error with a message."""
+    sc, ti, ri = _prepared("sam", workdir)
+    params = grb.api.polish_params(sc["ks"], 4, sc["cbf"], sc["bf"])
+    with _open(sc, ti, ri) as pin:
+        with pytest.raises(grb.GrbError, match="target id not in the target index"):
+            pin.serve_batches_host(params, sc["subsample"], [["t0", "no_such_target"]])
+    with pytest.raises(grb.GrbError, match="BAM"):
+        grb.api.PolishInputs(ti, os.path.join(sc["dir"], "x.bam"), sc["reads"], ri, 8.0)
+    with pytest.raises(grb.GrbError, match="cannot read"):
+        grb.api.PolishInputs(ti, os.path.join(sc["dir"], "missing.paf"), sc["reads"], ri, 8.0)
+    tsv = os.path.join(sc["dir"], "one.tsv")
+    with open(tsv, "w") as f:
+        f.write("r0 t0 5\n")
+    with pytest.raises(grb.GrbError, match="not positive"):
+        grb.api.PolishInputs(ti, tsv, sc["reads"], ri, 0.0)
+    with open(tsv, "w") as f:
+        f.write("r0 t0 five\n")
+    with pytest.raises(grb.GrbError, match="not a minimizer count"):
+        grb.api.PolishInputs(ti, tsv, sc["reads"], ri, 8.0)
+    # a mapped read that the mapped-sequence index does not know
+    short = os.path.join(sc["dir"], "short.idx")
+    with open(ri) as f, open(short, "w") as g:
+        g.writelines(f.readlines()[:3])
+    with grb.api.PolishInputs(ti, sc["mappings"], sc["reads"], short, sc["mx_max"]) as pin:
+        with pytest.raises(grb.GrbError, match="mapped read not in the mapped-sequence index"):
+            pin.serve_batches_host(params, sc["subsample"], sc["batches"])
+    with pytest.raises(grb.GrbError, match="cannot read"):
+        grb.api.polish_index_build(os.path.join(sc["dir"], "absent.fa"), os.path.join(sc["dir"], "a.idx"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_serve_batches_on_the_device_equals_the_references_serve_batch(name, workdir):
+    """grb_polish_serve_batches: index + mappings + planning + sequence fetch on the host, filters by
+    the kernels; every batch's Bloom filters byte for byte what the reference's serve_batch saved."""
+    sc, ti, ri = _prepared(name, workdir)
+    params = grb.api.polish_params(sc["ks"], 4, sc["cbf"], sc["bf"])
+    seeds = grb.make_seed_pattern("1011011110110111101101", 22, 16, 3)
+    with _open(sc, ti, ri) as pin, grb.Engine(seeds, genome_size=1000000, weight=16) as e:
+        got = e.polish_serve_batches(pin, params, sc["subsample"], sc["batches"])
+        with pytest.raises(grb.GrbError, match="target id not in the target index"):
+            e.polish_serve_batches(pin, params, sc["subsample"], [["nope"]])
+    assert hashlib.md5(got.tobytes()).hexdigest() == GOLDEN[name]["bfs_md5"]
+    if HAVE_REF:
+        assert (got == piu.ref_serve(sc, ti, ri)).all()
