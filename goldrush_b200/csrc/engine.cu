@@ -1440,20 +1440,57 @@ grb_polish_fill_batches(grb_ctx* c, const grb_polish_params* p, uint32_t n_batch
   }
   size_t free_b = 0, total_b = 0;
   GRB_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-  const uint64_t per_job = p->cbf_bytes + p->bf_bytes;
+  const uint64_t per_job = p->cbf_bytes + 2 * p->bf_bytes;
   const uint64_t n_jobs = (uint64_t)n_batches * p->n_k;
-  // as many jobs in flight as three quarters of the free device memory hold: a job is one thread,
-  // so the number of resident counting filters IS the parallelism (12 000 jobs on a 180 GB part)
+  // as many jobs in flight as three quarters of the free device memory hold: a job is one warp,
+  // so the number of resident counting filters IS the parallelism.  A call that would fit one wave
+  // is still cut in up to four (of at least 1024 jobs, which fill the part) so that a wave's Bloom
+  // filters travel back to the host under the next wave's kernel.
   const uint64_t budget = free_b / 4 * 3;
-  const uint64_t wave = std::max<uint64_t>(1, std::min<uint64_t>(n_jobs, budget / per_job));
-  DevBuf<uint8_t> d_cbf, d_bf;
+  uint64_t wave = std::max<uint64_t>(1, std::min<uint64_t>(n_jobs, budget / per_job));
+  const uint64_t kMinWave = 1024;
+  if (n_jobs >= 2 * kMinWave) {
+    wave = std::min(wave, std::max(kMinWave, (n_jobs + 3) / 4));
+  }
+  DevBuf<uint8_t> d_cbf, d_bf[2];
   GRB_CUDA(c, d_cbf.reserve_exact(wave * p->cbf_bytes, s));
-  GRB_CUDA(c, d_bf.reserve_exact(wave * p->bf_bytes, s));
+  GRB_CUDA(c, d_bf[0].reserve_exact(wave * p->bf_bytes, s));
+  GRB_CUDA(c, d_bf[1].reserve_exact(wave * p->bf_bytes, s));
+  if (!c->copy_stream) {
+    GRB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    GRB_CUDA(c, cudaEventCreateWithFlags(&c->ra_ready, cudaEventDisableTiming));
+    GRB_CUDA(c, cudaEventCreateWithFlags(&c->ra_free, cudaEventDisableTiming));
+  }
+  const cudaStream_t cs = c->copy_stream;
+  struct Events
+  {
+    cudaEvent_t filled[2] = { nullptr, nullptr }, copied[2] = { nullptr, nullptr };
+    ~Events()
+    {
+      for (int i = 0; i < 2; ++i) {
+        if (filled[i]) {
+          cudaEventDestroy(filled[i]);
+        }
+        if (copied[i]) {
+          cudaEventDestroy(copied[i]);
+        }
+      }
+    }
+  } ev;
+  for (int i = 0; i < 2; ++i) {
+    GRB_CUDA(c, cudaEventCreateWithFlags(&ev.filled[i], cudaEventDisableTiming));
+    GRB_CUDA(c, cudaEventCreateWithFlags(&ev.copied[i], cudaEventDisableTiming));
+  }
   c->tic();
-  for (uint64_t j0 = 0; j0 < n_jobs; j0 += wave) {
+  uint64_t wi = 0;
+  for (uint64_t j0 = 0; j0 < n_jobs; j0 += wave, ++wi) {
     const uint64_t n = std::min(wave, n_jobs - j0);
+    const int b = (int)(wi & 1);
+    if (wi >= 2) {
+      GRB_CUDA(c, cudaStreamWaitEvent(s, ev.copied[b], 0)); // the copy of wave wi - 2 has left this buffer
+    }
     GRB_CUDA(c, cudaMemsetAsync(d_cbf.p, 0, n * p->cbf_bytes, s));
-    GRB_CUDA(c, cudaMemsetAsync(d_bf.p, 0, n * p->bf_bytes, s));
+    GRB_CUDA(c, cudaMemsetAsync(d_bf[b].p, 0, n * p->bf_bytes, s));
     GrbPolishWave w;
     w.seqs = d_seqs.p;
     w.off = d_off.p;
@@ -1465,7 +1502,7 @@ grb_polish_fill_batches(grb_ctx* c, const grb_polish_params* p, uint32_t n_batch
     w.job0 = (uint32_t)j0;
     w.n_jobs = (uint32_t)n;
     w.cbf = d_cbf.p;
-    w.bf = d_bf.p;
+    w.bf = d_bf[b].p;
     w.cbf_bytes = p->cbf_bytes;
     w.cbf_inv = (uint64_t)(((unsigned __int128)1 << 64) / p->cbf_bytes);
     w.bf_bytes = p->bf_bytes;
@@ -1481,8 +1518,13 @@ grb_polish_fill_batches(grb_ctx* c, const grb_polish_params* p, uint32_t n_batch
         w, d_tables.p);
     }
     c->launches += 1;
-    GRB_CUDA(c, grb_copy_host(d_bf.p, (const char*)out_bfs + j0 * p->bf_bytes, n * p->bf_bytes, false, s));
-    GRB_CUDA(c, cudaStreamSynchronize(s));
+    GRB_CUDA(c, cudaEventRecord(ev.filled[b], s));
+    GRB_CUDA(c, cudaStreamWaitEvent(cs, ev.filled[b], 0));
+    GRB_CUDA(c, grb_copy_host(d_bf[b].p, (const char*)out_bfs + j0 * p->bf_bytes, n * p->bf_bytes, false, cs));
+    GRB_CUDA(c, cudaEventRecord(ev.copied[b], cs));
+  }
+  for (int b = 0; b < 2 && (uint64_t)b < wi; ++b) {
+    GRB_CUDA(c, cudaStreamWaitEvent(s, ev.copied[b], 0));
   }
   c->toc();
   int status = 0;

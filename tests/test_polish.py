@@ -116,9 +116,10 @@ def test_device_bloom_filters_match_the_reference_fixture(name):
 
 @pytest.mark.gpu
 def test_device_runs_many_batches_in_waves():
-    """More (batch, k) jobs than one wave holds with the reference's 10 MiB counting filters would
-    be slow to test; small filters and 300 batches exercise the wave loop and the job indexing."""
-    batches = pu.make_batches(31, n_batches=300, reads_per_batch=4, genome_len=4000, max_len=600)
+    """2 200 (batch, k) jobs with small filters: the call is cut into three waves (1024, 1024, 152
+    jobs), the Bloom filters of one travelling back under the kernel of the next through two
+    alternating device buffers; exercises the wave loop, the buffer reuse and the job indexing."""
+    batches = pu.make_batches(31, n_batches=1100, reads_per_batch=4, genome_len=4000, max_len=600)
     ks, h, cbf, bf = [31, 25], 3, 1 << 13, 1 << 10
     want = pu.port_fill(batches, ks, h, cbf, bf)
     seeds = grb.make_seed_pattern("1011011110110111101101", 22, 16, 3)
