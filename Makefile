@@ -2,7 +2,7 @@
 # goldrush_b200/meson.build and goldrush_path/meson.build describe the same targets for a reference
 # checkout, and tests/test_host_logic.py keeps the two descriptions in step).
 #
-#   make            libgoldrush_b200.so (CUDA, sm_100a) + goldrush-path + grb-synth
+#   make            libgoldrush_b200.so (CUDA, sm_100a) + goldrush-path + goldpolish-index + grb-synth
 #   make oracle     CPU checkers under oracle/ (test infrastructure)
 #   make host-tools grb-synth only (no CUDA needed)
 ROOT    := $(dir $(abspath $(lastword $(MAKEFILE_LIST))))
@@ -19,7 +19,7 @@ CU_SRC := $(wildcard $(ROOT)goldrush_b200/csrc/*.cu)
 CU_HDR := $(wildcard $(ROOT)goldrush_b200/csrc/*.cuh) $(wildcard $(ROOT)goldrush_b200/csrc/*.h) $(ROOT)include/goldrush_b200.h
 HOST_LIB_SRC := $(ROOT)goldrush_b200/host/synth.cpp $(ROOT)goldrush_b200/host/host_util.cpp $(ROOT)goldrush_b200/host/path_driver.cpp $(ROOT)goldrush_b200/host/decide_host.cpp $(ROOT)goldrush_b200/host/polish_driver.cpp $(ROOT)goldrush_b200/host/polish_inputs.cpp
 
-all: lib goldrush-path host-tools
+all: lib goldrush-path goldpolish-index host-tools
 
 lib: $(LIB)
 
@@ -32,6 +32,13 @@ goldrush-path: $(ROOT)build/goldrush-path
 $(ROOT)build/goldrush-path: $(ROOT)goldrush_b200/host/goldrush_path_main.cpp $(ROOT)goldrush_b200/host/opt.cpp $(LIB)
 	@mkdir -p $(ROOT)build
 	$(GRB_CXX) $(CXXFLAGS_HOST) -o $@ $(ROOT)goldrush_b200/host/goldrush_path_main.cpp $(ROOT)goldrush_b200/host/opt.cpp \
+	  -L$(LIBDIR) -lgoldrush_b200 -Wl,-rpath,'$$ORIGIN/../goldrush_b200/_lib'
+
+goldpolish-index: $(ROOT)build/goldpolish-index
+
+$(ROOT)build/goldpolish-index: $(ROOT)goldrush_b200/host/goldpolish_index_main.cpp $(LIB)
+	@mkdir -p $(ROOT)build
+	$(GRB_CXX) $(CXXFLAGS_HOST) -o $@ $(ROOT)goldrush_b200/host/goldpolish_index_main.cpp \
 	  -L$(LIBDIR) -lgoldrush_b200 -Wl,-rpath,'$$ORIGIN/../goldrush_b200/_lib'
 
 host-tools: $(ROOT)build/grb-synth
@@ -52,4 +59,4 @@ oracle:
 clean:
 	rm -rf $(ROOT)build $(LIBDIR)
 
-.PHONY: all lib goldrush-path host-tools tools oracle clean
+.PHONY: all lib goldrush-path goldpolish-index host-tools tools oracle clean

@@ -29,6 +29,14 @@ def shard_range(n, rank, world):
     return rank * n // world, (rank + 1) * n // world
 
 
+def polish_batch_share(n_batches, rank, world):
+    """(f4) GoldPolish Bloom-filter batches are independent objects (one OpenMP task each in the
+    reference, goldpolish_targeted_bfs.cpp:181-196): rank r serves batches r, r + W, r + 2W, ... with
+    its own grb_polish_serve_batches / grb_polish_fill_batches call and writes their filters itself.
+    No collective."""
+    return list(range(rank, n_batches, world))
+
+
 def tile_chunk(n_tiles, world):
     """Tiles per rank of one batch: the library pads a batch to world * tile_chunk tiles so that
     the all-gather is uniform; rank r owns tiles [r*chunk, min((r+1)*chunk, n_tiles))."""

@@ -79,6 +79,13 @@ def test_world2_gloo_pass1_or_reduce_and_plumbing(tmp_path):
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
 
 
+def test_polish_batches_are_dealt_to_ranks_exactly_once():
+    for world in (1, 2, 3, 8):
+        for n in (0, 1, 7, 64):
+            dealt = sorted(b for r in range(world) for b in multi.polish_batch_share(n, r, world))
+            assert dealt == list(range(n))
+
+
 def test_shares_cover_and_do_not_overlap():
     for n in (0, 1, 7, 128, 3201):
         for world in (1, 2, 3, 4, 8):

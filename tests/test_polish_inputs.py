@@ -145,6 +145,21 @@ def test_input_errors_are_reported_not_fatal(workdir):
         grb.api.polish_index_build(os.path.join(sc["dir"], "absent.fa"), os.path.join(sc["dir"], "a.idx"))
 
 
+def test_goldpolish_index_executable_is_a_drop_in(workdir):
+    """build/goldpolish-index: the reference tool's two arguments and its refusal of anything else
+    (goldpolish_index.cpp:6-9); the index it writes holds the reference's lines."""
+    import subprocess
+    exe = os.path.join(pu.ROOT, "build", "goldpolish-index")
+    sc = piu.make_files("paf", str(workdir))
+    out = os.path.join(sc["dir"], "cli.idx")
+    subprocess.check_call([exe, sc["reads"], out])
+    assert list(piu.sorted_lines_md5(out)) == GOLDEN["paf"]["mapped_index"]
+    p = subprocess.run([exe, sc["reads"]], capture_output=True)
+    assert p.returncode == 1 and p.stderr == b"Wrong args.\n"
+    p = subprocess.run([exe, os.path.join(sc["dir"], "absent.fq"), out], capture_output=True)
+    assert p.returncode == 1 and b"cannot read" in p.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", NAMES)
 def test_serve_batches_on_the_device_equals_the_references_serve_batch(name, workdir):
