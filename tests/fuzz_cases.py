@@ -36,3 +36,11 @@ def _case(i):
 
 
 CASES = [_case(i) for i in range(N_CASES)]
+# -P 0 with more than 50 000 long-enough reads: the median is taken over the first 50 000 (the
+# reference's counter stops one past the cap per thread, goldrush_path.cpp:91-103; the reference arm
+# of the CPU test runs with -j 2); the late reads are all Q40 so that a median over everything would differ
+CASES.append(dict(name="median_over_cap", synth=pu.golden_cases.synth_args(150000, 80, 220, 77, q="8,38"),
+                  post="late_reads_q40",
+                  args=["-k", "16", "-w", "10", "-h", "2", "-t", "100", "-b", "2", "-u", "1", "-a", "1", "-o",
+                        "0.1", "-x", "5", "-d", "9", "-P", "0", "-g", "150000", "-r", "0.9", "-M", "2", "-m",
+                        "200", "--silver_path", "--verbose"]))

@@ -112,7 +112,16 @@ ODD_K_CASE = dict(name="odd_k_aborts", synth=synth_args(60000, 10, 4000, 19),
                         "-a", "1", "-o", "0.1", "-x", "10", "-b", "5", "-d", "5", "-P", "0", "-g",
                         "6e4", "-r", "0.9", "-M", "3", "-m", "4000", "--silver_path", "--verbose"])
 
-POST = {"mutate_n_and_case": mutate_n_and_case, "ragged_tail": ragged_tail}
+def late_reads_q40(data: bytes) -> bytes:
+    """Every read after the 50 000th gets quality 'I' throughout: the -P 0 median must not see them
+    (MEDIAN_SAMPLES_NEEDED, goldrush_path.cpp:38,93-96), the filters of pass 1 and 2 must."""
+    lines = data.split(b"\n")
+    for i in range(50000 * 4 + 3, len(lines) - 1, 4):
+        lines[i] = b"I" * len(lines[i])
+    return b"\n".join(lines)
+
+
+POST = {"mutate_n_and_case": mutate_n_and_case, "ragged_tail": ragged_tail, "late_reads_q40": late_reads_q40}
 
 
 def md5(b: bytes) -> str:
