@@ -1380,19 +1380,25 @@ grbo_eval_flanks(int64_t ls, int64_t le, const uint32_t* ids, size_t n, uint64_t
 }
 
 uint64_t
-grbo_ntcard(const char* fastq_path, const char* const* seed_strs, unsigned h,
-            uint64_t* per_pattern)
+grbo_ntcard_sized(const char* fastq_path, const char* const* seed_strs, unsigned h, uint64_t file_bytes,
+                  uint64_t* per_pattern)
 {
   std::vector<Read> reads;
   bool is_fastq;
   load_fastq(fastq_path, reads, is_fastq);
   std::ifstream in(fastq_path, std::ifstream::ate | std::ifstream::binary);
-  const uint64_t bytes = (uint64_t)in.tellg();
+  const uint64_t bytes = file_bytes ? file_bytes : (uint64_t)in.tellg();
   std::vector<SeedTable> seeds;
   for (unsigned i = 0; i < h; ++i) {
     seeds.emplace_back(std::string(seed_strs[i]));
   }
   return ntcard_estimate(reads, bytes, seeds, per_pattern);
+}
+
+uint64_t
+grbo_ntcard(const char* fastq_path, const char* const* seed_strs, unsigned h, uint64_t* per_pattern)
+{
+  return grbo_ntcard_sized(fastq_path, seed_strs, h, 0, per_pattern);
 }
 
 int

@@ -77,6 +77,10 @@ int grbo_eval_flanks(int64_t ls, int64_t le, const uint32_t* ids, size_t n, uint
 /* ntcard.hpp:248-274 on a FASTQ file; per_pattern[h] may be NULL */
 uint64_t grbo_ntcard(const char* fastq_path, const char* const* seeds, unsigned h,
                      uint64_t* per_pattern);
+/* the same with the input size given (0 = the file's own): ntcard.hpp:180-183 picks sBits = 11 from
+ * 50 GB up, which no test file reaches */
+uint64_t grbo_ntcard_sized(const char* fastq_path, const char* const* seeds, unsigned h,
+                           uint64_t file_bytes, uint64_t* per_pattern);
 
 /* the whole stage with the reference's command line (goldrush_path.cpp:1096-1275); returns the
  * process exit code instead of calling exit() */

@@ -49,6 +49,8 @@ def lib():
         L.grbo_eval_flanks.argtypes = [C.c_int64, C.c_int64, vp, sz, P(u64), P(u64)]
         L.grbo_ntcard.restype = u64
         L.grbo_ntcard.argtypes = [C.c_char_p, P(C.c_char_p), C.c_uint, P(u64)]
+        L.grbo_ntcard_sized.restype = u64
+        L.grbo_ntcard_sized.argtypes = [C.c_char_p, P(C.c_char_p), C.c_uint, u64, P(u64)]
         _L = L
     return _L
 

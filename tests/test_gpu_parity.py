@@ -93,6 +93,27 @@ def test_ingest_decodes_ragged_fastq():
             assert (m.phred_first_half_sum, m.phred_total_sum) == (f0, t0)
 
 
+@pytest.mark.parametrize("input_bytes", [0, 60_000_000_000])
+def test_cardinality_estimate_matches_oracle_for_both_sample_widths(input_bytes, workdir):
+    """K5 (ntcard.hpp:81-154,180-188,248-274): the estimate per seed pattern and in total, with the
+    sample width the input size selects -- sBits = 7 below 50 GB (the file's own size here) and
+    sBits = 11 from 50 GB up, which no test file reaches, so the size is passed in on both sides."""
+    seeds = grb.make_seed_pattern(SEED22, 22, 16, 3)
+    sp = grb.api.synth_params(400000, 12.0, 5000, 57)
+    data = grb.synth_fastq(sp)
+    fq = os.path.join(workdir, "ntcard_widths.fq")
+    with open(fq, "wb") as f:
+        f.write(data)
+    L = ou.lib()
+    per = (ou.C.c_uint64 * 3)()
+    arr = (ou.C.c_char_p * 3)(*[s.encode() for s in seeds])
+    want_total = L.grbo_ntcard_sized(fq.encode(), arr, 3, input_bytes, per)
+    with grb.Engine(seeds, genome_size=400000, weight=16) as e:
+        e.reads_ingest_fastq(data)
+        got_per, got_total = e.estimate_cardinality(input_bytes or len(data))
+    assert got_per == list(per) and got_total == want_total and want_total > 0
+
+
 def test_ingest_readahead_equals_plain_ingest():
     """grb_reads_readahead: chunks copied ahead on the second stream (and re-aligned on the device)
     decode to exactly the same read store as chunks copied inside the call."""
