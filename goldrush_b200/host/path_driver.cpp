@@ -373,6 +373,15 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     return set_err(err, err_cap, "slice mode (fastq_total != 0) cannot write output files: no rank "
                                  "holds the whole input", GRB_ERR_ARG);
   }
+  // The reference opens (truncates) its first output file before pass 1 (goldrush_path.cpp:1174-1179):
+  // a run that stops later -- input not FASTQ, a read shorter than the seed span, no read passing the
+  // filters -- leaves that file behind, empty.
+  if (o->write_outputs) {
+    const std::string prefix0 = o->prefix ? o->prefix : "goldrush_out";
+    if (FILE* f0 = fopen((p.silver_path ? prefix0 + "_1.fq" : prefix0 + ".fa").c_str(), "wb")) {
+      fclose(f0);
+    }
+  }
   // byte `off` of the whole input, as this process can address it (slice mode: own reads only)
   const uint64_t data_origin = slice_mode ? o->fastq_offset : 0;
   bool early = false; // pass 1 already done chunk by chunk during the ingest
@@ -380,8 +389,45 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   double early_ms = 0;
   std::vector<uint8_t> early_flags;
 
+  // goldrush_path.cpp:1138-1161
+  auto log_parameters = [&]() {
+    log("Calculating %s\nUsing:\n\ttile length: %llu\n\tblock size: %llu\n\tseed patterns: %llu\n"
+        "\tthreshold: %llu\n\tbase seed pattern: %s\n\tminimum unassigned tiles: %llu\n"
+        "\tmaximum assigned tiles: %llu\n\texpected hash space: %llu\n"
+        "\tminimum average phred quality score: %u\n"
+        "\tmaximum average phred delta between first and second half of read: %u\n"
+        "\toccupancy: %g\n\tjobs: %d\n",
+        p.silver_path ? (std::to_string(p.max_paths) + " silver path(s)").c_str() : "the golden path",
+        (unsigned long long)p.tile_length, (unsigned long long)p.block_size,
+        (unsigned long long)p.hash_num, (unsigned long long)p.threshold, seed_c[0],
+        (unsigned long long)p.unassigned_min, (unsigned long long)p.assigned_max,
+        (unsigned long long)p.hash_universe, p.phred_min, p.phred_delta, p.occupancy, o->jobs);
+  };
+
+  // everything the reference has logged when fill_bit_vector starts reading (:1138-1199), for runs
+  // that end there before this driver's own logging has reached that point
+  auto log_up_to_pass1 = [&]() {
+    if (p.hash_universe == 0) {
+      p.hash_universe = grb_default_hash_universe(p.weight, p.genome_size, p.hash_num);
+    }
+    log_parameters();
+    if (o->filter_file && o->filter_file[0]) {
+      log("Using only reads not found in: %s\n", o->filter_file);
+    }
+    log("allocating bit vector\nm_filterSize: %llu\nfinished allocating bit vector\n"
+        "opening: %s\ninserting bit vector\n",
+        (unsigned long long)grb_calc_optimal_size(p.hash_universe, 1, p.occupancy),
+        o->input_path ? o->input_path : "(memory)");
+  };
+
   // ---- K1: one pass over the file ----
   if (n == 0 || data[0] != '@') {
+    // The reference meets its format check inside fill_bit_vector, after it has logged its parameters
+    // and sized the filter (goldrush_path.cpp:1109-1199): the same lines first, where they do not
+    // depend on reading the input (-H or -g sizing, -P given).
+    if (!(p.hash_universe == 0 && o->ntcard) && p.phred_min != 0) {
+      log_up_to_pass1();
+    }
     log("Gold Path requires fastq format\n"); // goldrush_path.cpp:247-250
     return set_err(err, err_cap, "Gold Path requires fastq format", GRB_ERR_FORMAT);
   }
@@ -476,6 +522,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
           const uint64_t my_hi = shard_ingest ? now : early_done + cnt * (uint64_t)(c_rank + 1) / (uint64_t)c_world;
           if ((rc = grb_reads_set_flags(ctx, early_done, cnt, early_flags.data() + early_done)) != GRB_OK ||
               (rc = grb_build_bitvector_range(ctx, my_lo, my_hi - my_lo)) != GRB_OK) {
+            log_up_to_pass1(); // a read shorter than the seed span: the reference dies inside pass 1
             log("%s\n", grb_last_error(ctx));
             return fail(rc);
           }
@@ -574,17 +621,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
   }
   R.phred_min = p.phred_min;
 
-  log("Calculating %s\nUsing:\n\ttile length: %llu\n\tblock size: %llu\n\tseed patterns: %llu\n"
-      "\tthreshold: %llu\n\tbase seed pattern: %s\n\tminimum unassigned tiles: %llu\n"
-      "\tmaximum assigned tiles: %llu\n\texpected hash space: %llu\n"
-      "\tminimum average phred quality score: %u\n"
-      "\tmaximum average phred delta between first and second half of read: %u\n"
-      "\toccupancy: %g\n\tjobs: %d\n",
-      p.silver_path ? (std::to_string(p.max_paths) + " silver path(s)").c_str() : "the golden path",
-      (unsigned long long)p.tile_length, (unsigned long long)p.block_size,
-      (unsigned long long)p.hash_num, (unsigned long long)p.threshold, seed_c[0],
-      (unsigned long long)p.unassigned_min, (unsigned long long)p.assigned_max,
-      (unsigned long long)p.hash_universe, p.phred_min, p.phred_delta, p.occupancy, o->jobs);
+  log_parameters();
 
   // ---- name filter (-f, goldrush_path.cpp:1163-1172) ----
   std::unordered_set<std::string> filter_out;

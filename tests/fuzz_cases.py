@@ -44,3 +44,38 @@ CASES.append(dict(name="median_over_cap", synth=pu.golden_cases.synth_args(15000
                   args=["-k", "16", "-w", "10", "-h", "2", "-t", "100", "-b", "2", "-u", "1", "-a", "1", "-o",
                         "0.1", "-x", "5", "-d", "9", "-P", "0", "-g", "150000", "-r", "0.9", "-M", "2", "-m",
                         "200", "--silver_path", "--verbose"]))
+
+
+# ---- degenerate inputs (golden mode, -m 0: nothing is filtered by length) ----
+EDGE_ARGS = ["-k", "22", "-w", "16", "-h", "3", "-t", "500", "-b", "3", "-u", "2", "-a", "1", "-o", "0.1", "-x",
+             "8", "-d", "5", "-P", "15", "-g", "30000", "-m", "0", "--verbose"]
+
+
+def edge_inputs():
+    """name -> FASTQ text.  An empty file and a file holding one newline are "not FASTQ" (exit 1,
+    goldrush_path.cpp:247-250); a read shorter than the seed span ends the run in SeedNtHash (exit 1,
+    after the output file was opened); reads of less than one tile and of exactly one tile are
+    processed."""
+    import random
+    rnd = random.Random(3)
+
+    def seq(n):
+        return "".join(rnd.choice("ACGT") for _ in range(n))
+
+    def rec(name, s):
+        return f"@{name}\n{s}\n+\n{'I' * len(s)}\n"
+
+    g = seq(30000)
+    base = "".join(rec(f"r{i}", g[st:st + 3000]) for i, st in enumerate(range(0, 27000, 700)))
+    last = rec("r_last", g[100:3100])
+    return {
+        "empty_file": "",
+        "one_newline": "\n",
+        "read_shorter_than_k": base + rec("tiny", seq(10)) + last,
+        "read_shorter_than_a_tile": base + rec("sub", seq(450)) + last,
+        "read_of_exactly_one_tile": base + rec("one", g[5000:5500]) + last,
+        "no_final_newline": (base + last)[:-1],
+    }
+
+
+EDGE_EXIT = {"empty_file": 1, "one_newline": 1, "read_shorter_than_k": 1}

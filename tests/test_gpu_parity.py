@@ -375,6 +375,22 @@ def test_parameter_fuzz_cli_equals_oracle(case, workdir):
     assert pu.parse_stats(err_g) == pu.parse_stats(err_o)
 
 
+@pytest.mark.parametrize("name", sorted(fuzz_cases.edge_inputs()))
+def test_degenerate_inputs_cli_equals_oracle(name, workdir):
+    """Empty and one-newline files, reads shorter than k / than a tile / of exactly one tile, a last
+    record without newline: the drop-in executable exits as the oracle does (which the CPU suite
+    holds against the reference's own sources) and writes the same files and counters."""
+    inp = os.path.join(workdir, name + ".fq")
+    with open(inp, "w") as f:
+        f.write(fuzz_cases.edge_inputs()[name])
+    case = dict(name="edge_" + name, args=fuzz_cases.EDGE_ARGS)
+    rc_o, outs_o, err_o = pu.run_cli(pu.ORACLE, case, inp, [], workdir, "ora", jobs=2)
+    rc_g, outs_g, err_g = pu.run_cli(pu.PRODUCT, case, inp, [], workdir, "gpu", jobs=2)
+    assert rc_g == rc_o == fuzz_cases.EDGE_EXIT.get(name, 0), err_g[-2000:]
+    assert pu.digest_outputs(outs_g) == pu.digest_outputs(outs_o)
+    assert pu.parse_stats(err_g) == pu.parse_stats(err_o)
+
+
 @pytest.mark.parametrize("pair", [("silver_default", "golden_default"), ("silver_m12", "golden_m12")])
 def test_two_stage_call_equals_two_reference_runs(pair, workdir):
     """grb_run_two_stage (bin/goldrush:240-260 in one call): the silver files of the silver case

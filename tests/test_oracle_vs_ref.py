@@ -53,6 +53,23 @@ def test_parameter_fuzz_oracle_equals_reference_binary(case, workdir):
     assert pu.parse_stats(err_r) == pu.parse_stats(err_o)
 
 
+@pytest.mark.parametrize("name", sorted(fuzz_cases.edge_inputs()))
+def test_degenerate_inputs_oracle_equals_reference_binary(name, workdir):
+    """Empty and one-newline files, reads shorter than k / than a tile / of exactly one tile, a last
+    record without newline: same exit code, same files, same counters."""
+    inp = os.path.join(workdir, name + ".fq")
+    with open(inp, "w") as f:
+        f.write(fuzz_cases.edge_inputs()[name])
+    case = dict(name="edge_" + name, args=fuzz_cases.EDGE_ARGS)
+    rc_r, outs_r, err_r = pu.run_cli(pu.REF, case, inp, [], workdir, "ref", jobs=2)
+    rc_o, outs_o, err_o = pu.run_cli(pu.ORACLE, case, inp, [], workdir, "ora", jobs=2)
+    assert rc_r == rc_o == fuzz_cases.EDGE_EXIT.get(name, 0), (err_r[-300:], err_o[-300:])
+    assert pu.digest_outputs(outs_r) == pu.digest_outputs(outs_o)
+    assert pu.parse_stats(err_r) == pu.parse_stats(err_o)
+    if rc_r == 0:
+        assert outs_r and os.path.getsize(outs_r[0]) > 0
+
+
 def test_odd_k_aborts_in_reference_and_oracle(workdir):
     """An odd -k gives seeds of span k - 1 and the reference dies on the assertion in the filter's
     constructor (MIBloomFilter.hpp:180) after pass 1; the oracle mirrors that, the engine refuses
