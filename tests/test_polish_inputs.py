@@ -113,6 +113,85 @@ def test_minimizer_filter_fuzz_against_the_reference(seed, workdir):
     assert kept > 0
 
 
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built here")
+@pytest.mark.parametrize("seed", range(6))
+def test_index_build_fuzz_against_the_reference(seed, workdir):
+    """goldpolish-index on odd but legal files: ids followed by blanks, tabs or nothing, descriptions
+    holding '@' and '>', quality lines that begin with '@' or '+', one-character reads (the Phred
+    average is taken over all but the last character, over the one character when there is only one),
+    repeated ids, a last line without newline; FASTQ and two-line FASTA."""
+    rnd = random.Random(600 + seed)
+    d = os.path.join(str(workdir), f"idx{seed}")
+    os.makedirs(d, exist_ok=True)
+    fastq = seed % 2 == 0
+    path = os.path.join(d, "s.fq" if fastq else "s.fa")
+    recs = []
+    for i in range(rnd.randint(20, 60)):
+        rid = rnd.choice([f"s{i}", f"s{i}", f"s{rnd.randint(0, i)}", f"x|{i}.1", f"{i}"])
+        sep = rnd.choice(["", " ", "  two blanks", "\tafter a tab", " desc @with >signs", "\t", " \tmix"])
+        ln = rnd.choice([1, 2, 3, 50, 400])
+        s = "".join(rnd.choice("ACGTNacgt") for _ in range(ln))
+        if fastq:
+            q = "".join(chr(rnd.randint(33, 74)) for _ in range(ln))
+            if rnd.random() < 0.3:
+                q = rnd.choice("@+") + q[1:]
+            recs.append(f"@{rid}{sep}\n{s}\n+{rnd.choice(['', rid])}\n{q}\n")
+        else:
+            recs.append(f">{rid}{sep}\n{s}\n")
+    text = "".join(recs)
+    if rnd.random() < 0.5:
+        text = text[:-1]
+    with open(path, "w") as f:
+        f.write(text)
+    mine, ref = os.path.join(d, "mine.idx"), os.path.join(d, "ref.idx")
+    grb.api.polish_index_build(path, mine)
+    piu.ref_index(path, ref)
+    with open(mine, "rb") as f, open(ref, "rb") as g:
+        assert sorted(f.read().splitlines()) == sorted(g.read().splitlines())
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built here")
+@pytest.mark.parametrize("fmt,seed", [("paf", 0), ("paf", 1), ("sam", 0), ("sam", 1)])
+def test_alignment_loader_fuzz_against_the_reference(fmt, seed, workdir):
+    """load_paf / load_sam (mappings.cpp:109-224) on ragged files: header lines, blank lines, lines too
+    short to hold the target column (they inherit the target of the line before), repeated pairs,
+    targets outside the index, blanks and tabs mixed as separators."""
+    rnd = random.Random(700 + seed + (10 if fmt == "sam" else 0))
+    d = os.path.join(str(workdir), f"aln_{fmt}{seed}")
+    os.makedirs(d, exist_ok=True)
+    tidx, midx, seqs = (os.path.join(d, n) for n in ("t.idx", "m.idx", "none.fq"))
+    open(seqs, "w").close()
+    open(midx, "w").close()
+    targets = [f"c{i}" for i in range(8)]
+    with open(tidx, "w") as f:
+        for t in targets:
+            f.write(f"{t}\t0\t{rnd.randint(500, 90000)}\t0\n")
+    mp = os.path.join(d, "aln." + fmt)
+    with open(mp, "w") as f:
+        for n in range(300):
+            q, t = f"q{rnd.randint(0, 60)}", rnd.choice(targets + ["other", "c1"])
+            x = rnd.random()
+            sep = rnd.choice(["\t", " ", "\t\t"])
+            if x < 0.05:
+                f.write("@PG\tID:x\n")
+            elif x < 0.1:
+                f.write("\n")
+            elif x < 0.2:
+                f.write(sep.join([q, "16"]) + "\n")
+            elif fmt == "paf":
+                f.write(sep.join([q, "900", "0", "900", "+", t, "5000", "1", "901", "880", "900", "60"]) + "\n")
+            else:
+                f.write(sep.join([q, "0", t, "7", "60", "900M", "*", "0", "0", "*", "*"]) + "\n")
+    sc = dict(targets=seqs, mappings=mp, mx_max=8.0)
+    kept = 0
+    with grb.api.PolishInputs(tidx, mp, seqs, midx, 8.0) as pin:
+        for t in targets + ["other"]:
+            mine = pin.mappings(t)
+            assert mine == piu.ref_mappings(sc, tidx, t), t
+            kept += len(mine)
+    assert kept > 50
+
+
 def test_input_errors_are_reported_not_fatal(workdir):
     """Where the reference dies (uncaught std::out_of_range from .at(), exit(1) from check_error), the
     library returns an error with a message."""
