@@ -26,6 +26,8 @@ def built():
         need.append("lib")
     if not os.path.exists(os.path.join(ROOT, "build", "goldrush-path")):
         need.append("goldrush-path")
+    if not os.path.exists(os.path.join(ROOT, "build", "goldpolish-index")):
+        need.append("goldpolish-index")
     if need:
         subprocess.check_call(["make", "-s", "-C", ROOT] + need)
     return True
