@@ -373,15 +373,18 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     return set_err(err, err_cap, "slice mode (fastq_total != 0) cannot write output files: no rank "
                                  "holds the whole input", GRB_ERR_ARG);
   }
-  // The reference opens (truncates) its first output file before pass 1 (goldrush_path.cpp:1174-1179):
-  // a run that stops later -- input not FASTQ, a read shorter than the seed span, no read passing the
-  // filters -- leaves that file behind, empty.
-  if (o->write_outputs) {
-    const std::string prefix0 = o->prefix ? o->prefix : "goldrush_out";
-    if (FILE* f0 = fopen((p.silver_path ? prefix0 + "_1.fq" : prefix0 + ".fa").c_str(), "wb")) {
-      fclose(f0);
+  // The reference opens (truncates) its first output file after sizing and before pass 1
+  // (goldrush_path.cpp:1109-1123,1174-1179): a run that stops later -- input not FASTQ, a read shorter
+  // than the seed span, no read passing the filters -- leaves that file behind, empty; a run that dies
+  // inside --ntcard sizing does not.
+  auto touch_first_output = [&]() {
+    if (o->write_outputs) {
+      const std::string prefix0 = o->prefix ? o->prefix : "goldrush_out";
+      if (FILE* f0 = fopen((p.silver_path ? prefix0 + "_1.fq" : prefix0 + ".fa").c_str(), "wb")) {
+        fclose(f0);
+      }
     }
-  }
+  };
   // byte `off` of the whole input, as this process can address it (slice mode: own reads only)
   const uint64_t data_origin = slice_mode ? o->fastq_offset : 0;
   bool early = false; // pass 1 already done chunk by chunk during the ingest
@@ -428,6 +431,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
     if (!(p.hash_universe == 0 && o->ntcard) && p.phred_min != 0) {
       log_up_to_pass1();
     }
+    touch_first_output();
     log("Gold Path requires fastq format\n"); // goldrush_path.cpp:247-250
     return set_err(err, err_cap, "Gold Path requires fastq format", GRB_ERR_FORMAT);
   }
@@ -523,6 +527,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
           if ((rc = grb_reads_set_flags(ctx, early_done, cnt, early_flags.data() + early_done)) != GRB_OK ||
               (rc = grb_build_bitvector_range(ctx, my_lo, my_hi - my_lo)) != GRB_OK) {
             log_up_to_pass1(); // a read shorter than the seed span: the reference dies inside pass 1
+            touch_first_output();
             log("%s\n", grb_last_error(ctx));
             return fail(rc);
           }
@@ -571,6 +576,7 @@ run_path_impl(const grb_run_options* o, const char* fastq, size_t fastq_len, grb
       p.hash_universe = grb_default_hash_universe(p.weight, p.genome_size, p.hash_num);
     }
   }
+  touch_first_output();
 
   // host threads for the bookkeeping loops: -j if given, else the machine's cores divided by the
   // ranks sharing it (one process per GPU).  Set explicitly on every region: launchers such as
