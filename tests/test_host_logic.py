@@ -12,6 +12,7 @@ import pytest
 
 import goldrush_b200 as grb
 import oracle_util as ou
+import parity_util as pu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -316,3 +317,31 @@ def test_grouped_hash_code_matches_oracle_on_host(k, w, h, preset):
         rc = grb.lib().grb_test_group_hash_host(arr, h, seq, n, out.ctypes.data)
         assert rc == 0
         assert np.array_equal(out.reshape(-1, h), want), (n, k, h)
+
+
+@pytest.mark.skipif(not os.path.exists(pu.REF), reason="oracle/_ref not built here")
+def test_command_line_refusals_match_the_reference_binary():
+    """process_options (opt.cpp:90-217) needs no GPU: --help and every refusal that is decided before
+    the input is opened give the same exit code, the same stdout and the same stderr as the
+    reference's own opt.cpp (getopt's own diagnostics name the executable, so those compare by exit
+    code only)."""
+    import subprocess
+    seed = "1011011110110111101101"
+    lines = [
+        ["--help"],
+        [],
+        ["-i", "x.fq", "-w", "16", "-g", "1000"],                        # span 0
+        ["-i", "x.fq", "-k", "22", "-g", "1000"],                        # weight 0
+        ["-i", "x.fq", "-k", "22", "-w", "16"],                          # genome size 0
+        ["-i", "x.fq", "-k", "20", "-w", "16", "-g", "1000", "-s", seed],  # preset longer than k
+        ["-i", "x.fq", "-k", "22", "-w", "14", "-g", "1000", "-s", seed],  # preset weight != w
+        ["-i", "x.fq", "-k", "22", "-w", "16", "-g", "0"],
+    ]
+    for args in lines:
+        r = subprocess.run([pu.REF] + args, capture_output=True)
+        g = subprocess.run([pu.PRODUCT] + args, capture_output=True)
+        assert (g.returncode, g.stdout, g.stderr) == (r.returncode, r.stdout, r.stderr), args
+    for args in (["-z"], ["--no_such_option"], ["-k"]):
+        r = subprocess.run([pu.REF] + args, capture_output=True)
+        g = subprocess.run([pu.PRODUCT] + args, capture_output=True)
+        assert g.returncode == r.returncode == 1, args
